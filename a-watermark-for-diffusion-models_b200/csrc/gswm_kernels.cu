@@ -1,0 +1,575 @@
+// libgswm device entry points: ChaCha20 keystream (K1), embed (K2), extract (K3) for sm_100a.
+//
+// Work decomposition shared by K2/K3: a TILE is 32 consecutive ChaCha20 blocks of one latent =
+// 16384 latent elements = 2 KB of keystream = 64 KB of fp32 latent.  One warp produces a tile's
+// keystream with one ChaCha block per lane (no shuffles: a quarter-round is 12 register ops); the
+// CTA's 256 threads then stream the tile as 16 fully coalesced 128-bit accesses per thread.
+//
+// HBM layout: latents are [n_latents][n_elems] contiguous (C-order (B,4,H/8,W/8)), 16-byte aligned;
+// keys [.][32], nonces [.][16], messages [.][msg_bits/8] are byte arrays; the shared-key workspace
+// holds one latent's worth of keystream (embed: keystream XOR tiled message), n_elems/8 bytes.
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/gswm.h"
+#include "gswm_math.cuh"
+
+namespace gswm {
+
+constexpr int kThreads = 256;
+constexpr int kTileElems = 16384;            // 32 ChaCha blocks
+constexpr int kTileWords = kTileElems / 32;  // 512 keystream words
+constexpr int kTileF4 = kTileElems / 4;      // 4096 float4 per tile
+
+static std::atomic<int64_t> g_launches{0};
+
+// Reference extract.py:83: int(norm.cdf(z) * 2) == 1  <=>  z >= -6.957291061679417e-17 (float64).
+// Smallest fp32 that is >= that double; for fp16/bf16 inputs the comparison is simply z >= 0
+// because no half/bfloat16 value lies in [-6.96e-17, 0) other than -0.0 (which is >= the threshold).
+__device__ __forceinline__ float quantise_threshold() { return __uint_as_float(0xA4A06C98u); }
+
+__device__ __forceinline__ void load_key_nonce(const uint8_t* __restrict__ keys, const uint8_t* __restrict__ nonces,
+                                               int64_t row, uint32_t (&k)[8], uint32_t (&n)[4]) {
+  const uint32_t* kp = reinterpret_cast<const uint32_t*>(keys + row * 32);
+  const uint32_t* np = reinterpret_cast<const uint32_t*>(nonces + row * 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k[i] = __ldg(kp + i);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) n[i] = __ldg(np + i);
+}
+
+// Message word for keystream word index `wi` of a latent: the message tiled n_elems/msg_bits times,
+// zero beyond the last whole copy (nodes.py:79-87).
+__device__ __forceinline__ uint32_t tiled_msg_word(const uint8_t* __restrict__ msg, uint32_t wi, uint32_t msg_words,
+                                                   uint32_t tiled_words) {
+  if (msg == nullptr || wi >= tiled_words) return 0u;
+  return __ldg(reinterpret_cast<const uint32_t*>(msg) + (wi % msg_words));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: keystream (optionally XOR tiled message) to global memory, one ChaCha block per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+chacha20_keystream_kernel(const uint8_t* __restrict__ keys, const uint8_t* __restrict__ nonces,
+                          const uint8_t* __restrict__ msgs, int64_t n_streams, uint32_t blocks_each,
+                          uint32_t msg_words, uint32_t tiled_words, uint32_t msg_stride_bytes,
+                          uint32_t* __restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (gid >= n_streams * (int64_t)blocks_each) return;
+  const int64_t s = gid / blocks_each;
+  const uint32_t blk = (uint32_t)(gid - s * blocks_each);
+  uint32_t k[8], n[4], ks[16];
+  load_key_nonce(keys, nonces, s, k, n);
+  chacha20_block(k, n, blk, ks);
+  const uint8_t* msg = msgs ? msgs + s * (int64_t)msg_stride_bytes : nullptr;
+  uint4* dst = reinterpret_cast<uint4*>(out + gid * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 v;
+    v.x = ks[4 * q + 0] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 0, msg_words, tiled_words);
+    v.y = ks[4 * q + 1] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 1, msg_words, tiled_words);
+    v.z = ks[4 * q + 2] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 2, msg_words, tiled_words);
+    v.w = ks[4 * q + 3] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 3, msg_words, tiled_words);
+    dst[q] = v;
+  }
+}
+
+// Fill a tile's keystream words in shared memory.
+//  kPerLatent: warp 0 computes them (lane = ChaCha block);  else: copy the slice of the precomputed
+//  table (workspace).  `words` = number of valid words in this tile (multiple of 16).
+template <bool kPerLatent>
+__device__ __forceinline__ void stage_tile_keystream(uint32_t* __restrict__ s_ks, const uint8_t* __restrict__ keys,
+                                                     const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
+                                                     const uint32_t* __restrict__ table, int64_t latent, uint32_t tile,
+                                                     uint32_t words, uint32_t msg_words, uint32_t tiled_words) {
+  if constexpr (kPerLatent) {
+    if (threadIdx.x < 32 && threadIdx.x * 16 < words) {
+      uint32_t k[8], n[4], ks[16];
+      load_key_nonce(keys, nonces, latent, k, n);
+      const uint32_t blk = tile * 32 + threadIdx.x;
+      chacha20_block(k, n, blk, ks);
+      // lane-strided 16-byte stores: lane l owns words [16 l, 16 l + 16)
+      uint4* dst = reinterpret_cast<uint4*>(s_ks + threadIdx.x * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 v;
+        v.x = ks[4 * q + 0] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 0, msg_words, tiled_words);
+        v.y = ks[4 * q + 1] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 1, msg_words, tiled_words);
+        v.z = ks[4 * q + 2] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 2, msg_words, tiled_words);
+        v.w = ks[4 * q + 3] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 3, msg_words, tiled_words);
+        dst[q] = v;
+      }
+    }
+  } else {
+    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)tile * kTileWords);
+    if (threadIdx.x * 4 < words) reinterpret_cast<uint4*>(s_ks)[threadIdx.x] = __ldg(src + threadIdx.x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: embed.  grid = n_latents * tiles_per_latent CTAs, one tile each.
+//   bits  <- keystream XOR tiled message                                (gs_insert.py:23,45-49)
+//   u     <- Philox4x32-10 word, 23 bits                               (stands in for gs_insert.py:62)
+//   z     <- Phi^-1((u + y)/2) via bucket_quantile_f32                  (gs_insert.py:64)
+//   store <- one 128-bit store per 4 elements, C-order flat index       (gs_insert.py:65)
+// ------------------------------------------------------------------------------------------------
+struct EmbedArgs {
+  const uint8_t* keys;
+  const uint8_t* nonces;
+  const uint8_t* msgs;
+  const uint32_t* table;     // shared-key bucket-bit table (keystream ^ tiled message)
+  float* out;
+  int64_t n_elems;
+  int64_t first_latent;      // global index of latent 0 (sharding)
+  uint32_t tiles_per_latent;
+  uint32_t msg_words;
+  uint32_t tiled_words;
+  uint32_t msg_stride_bytes;
+  uint32_t seed_lo, seed_hi, off_lo, off_hi;
+};
+
+template <bool kPerLatent>
+__global__ void __launch_bounds__(kThreads)
+embed_kernel(const EmbedArgs a) {
+  __shared__ __align__(16) uint32_t s_ks[kTileWords];
+  const int64_t latent = blockIdx.x / a.tiles_per_latent;
+  const uint32_t tile = blockIdx.x - (uint32_t)latent * a.tiles_per_latent;
+  const int64_t tile_base = (int64_t)tile * kTileElems;
+  const int64_t remain = a.n_elems - tile_base;
+  const uint32_t n_f4 = (uint32_t)(remain < kTileElems ? remain : kTileElems) >> 2;   // multiple of 128
+
+  const uint8_t* msg = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
+  stage_tile_keystream<kPerLatent>(s_ks, a.keys, a.nonces, msg, a.table, latent, tile, n_f4 >> 3,
+                                   a.msg_words, a.tiled_words);
+  __syncthreads();
+
+  const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
+  // global group index of this tile's first float4 (Philox counter), 64-bit
+  const uint64_t g0 = (uint64_t)((a.first_latent + latent) * a.n_elems + tile_base) >> 2;
+  float4* out4 = reinterpret_cast<float4*>(a.out + latent * a.n_elems + tile_base);
+
+  const uint32_t nib_shift = (threadIdx.x & 1u) ? 0u : 4u;
+#pragma unroll 2
+  for (uint32_t i = threadIdx.x; i < n_f4; i += kThreads) {
+    const uint64_t g = g0 + i;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), a.off_lo, a.off_hi),
+                                  a.seed_lo, a.seed_hi);
+    // 4 bucket bits of elements 4i..4i+3: byte i>>1, high nibble first (MSB-first bit order);
+    // i & 1 == threadIdx.x & 1 for every iteration, so the nibble shift is loop-invariant.
+    const uint32_t nib = (uint32_t)s_bytes[i >> 1] >> nib_shift;     // bits 3..0 = elements 0..3
+    uint32_t f0, f1, f2, f3;
+    nibble_flip_masks(nib, f0, f1, f2, f3);
+    const float4 z = bucket_quantile4_f32(r, f0, f1, f2, f3);
+    out4[i] = z;
+  }
+}
+
+// Injected-uniform embed (fp64 arithmetic, parity / seeded drop-in mode; not the throughput path).
+template <bool kPerLatent, typename OutT>
+__global__ void __launch_bounds__(kThreads)
+embed_injected_kernel(const EmbedArgs a, const double* __restrict__ u, int u_per_latent, OutT* __restrict__ out) {
+  __shared__ __align__(16) uint32_t s_ks[kTileWords];
+  const int64_t latent = blockIdx.x / a.tiles_per_latent;
+  const uint32_t tile = blockIdx.x - (uint32_t)latent * a.tiles_per_latent;
+  const int64_t tile_base = (int64_t)tile * kTileElems;
+  const int64_t remain = a.n_elems - tile_base;
+  const uint32_t n_el = (uint32_t)(remain < kTileElems ? remain : kTileElems);
+  const uint8_t* msg = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
+  stage_tile_keystream<kPerLatent>(s_ks, a.keys, a.nonces, msg, a.table, latent, tile, n_el >> 5,
+                                   a.msg_words, a.tiled_words);
+  __syncthreads();
+  const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
+  const double* up = u + (u_per_latent ? latent * a.n_elems : 0) + tile_base;
+  OutT* op = out + latent * a.n_elems + tile_base;
+  for (uint32_t e = threadIdx.x; e < n_el; e += kThreads) {
+    const double y = (double)((s_bytes[e >> 3] >> (7 - (e & 7))) & 1u);
+    const double p = (up[e] + y) / 2.0;                              // gs_insert.py:64, same roundings
+    op[e] = (OutT)norm_ppf_f64(p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: extract.  grid = n_latents CTAs (one latent each, looping over its tiles).
+//   bit    <- z >= threshold                                             (extract.py:82-84)
+//   bit    ^= keystream bit                                              (extract.py:86-87)
+//   count  <- per message position over the R copies                     (extract.py:91-98)
+//   msg    <- count > R/2  (strict; tie -> 0)                            (extract.py:99)
+//   score  <- popc(~(msg ^ reference))                                   (extract.py:103-109)
+// Fast path (kPow2): msg_bits divides 1024, so a thread's four positions never change and the four
+// counts ride in one register as byte lanes.  General path: shared-memory atomics per set bit.
+// ------------------------------------------------------------------------------------------------
+struct ExtractArgs {
+  const uint8_t* keys;
+  const uint8_t* nonces;
+  const uint8_t* msgs;        // reference messages (may be null)
+  const uint32_t* table;      // shared-key keystream table
+  const void* z;
+  uint8_t* msg_out;
+  uint16_t* counts;
+  int32_t* matched;
+  unsigned long long* counters;
+  int64_t n_elems;
+  uint32_t tiles_per_latent;
+  uint32_t msg_bits;
+  uint32_t msg_stride_bytes;
+  uint32_t copies;            // R = n_elems / msg_bits
+};
+
+template <typename T>
+struct ZLoad;   // loads 4 consecutive elements as float4 from a 4-element-group index
+
+template <>
+struct ZLoad<float> {
+  static __device__ __forceinline__ float4 ld(const void* base, size_t g) {
+    return __ldcs(reinterpret_cast<const float4*>(base) + g);
+  }
+};
+template <>
+struct ZLoad<__half> {
+  static __device__ __forceinline__ float4 ld(const void* base, size_t g) {
+    const uint2 r = __ldcs(reinterpret_cast<const uint2*>(base) + g);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+template <>
+struct ZLoad<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld(const void* base, size_t g) {
+    const uint2 r = __ldcs(reinterpret_cast<const uint2*>(base) + g);
+    // bf16 -> fp32 is a 16-bit left shift
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u),
+                       __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xFFFF0000u));
+  }
+};
+
+__device__ __forceinline__ uint32_t quantise_nibble(const float4 z, const float thr) {
+  // bits 3..0 = elements 0..3 (MSB-first, as the keystream nibble is laid out)
+  return (z.x >= thr ? 8u : 0u) | (z.y >= thr ? 4u : 0u) | (z.z >= thr ? 2u : 0u) | (z.w >= thr ? 1u : 0u);
+}
+
+template <typename T, bool kPerLatent, bool kPow2>
+__global__ void __launch_bounds__(kThreads)
+extract_kernel(const ExtractArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* s_ks = smem;                       // kTileWords
+  uint32_t* s_cnt = smem + kTileWords;         // msg_bits counters
+  __shared__ int s_matched;
+
+  const int64_t latent = blockIdx.x;
+  const float thr = quantise_threshold();
+  const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
+  const size_t z_g0 = (size_t)latent * (size_t)(a.n_elems >> 2);
+
+  for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) s_cnt[p] = 0;
+  if (threadIdx.x == 0) s_matched = 0;
+
+  uint32_t packed = 0;                          // kPow2: byte lane k = count of element (3-k)
+  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;      // spilled byte lanes (only for very large latents)
+  uint32_t iters_since_spill = 0;
+
+  for (uint32_t tile = 0; tile < a.tiles_per_latent; ++tile) {
+    const int64_t tile_base = (int64_t)tile * kTileElems;
+    const int64_t remain = a.n_elems - tile_base;
+    const uint32_t n_f4 = (uint32_t)(remain < kTileElems ? remain : kTileElems) >> 2;
+    __syncthreads();                            // previous tile's keystream no longer needed
+    stage_tile_keystream<kPerLatent>(s_ks, a.keys, a.nonces, nullptr, a.table, latent, tile, n_f4 >> 3, 0, 0);
+    __syncthreads();
+    const size_t zt = z_g0 + (size_t)(tile_base >> 2);
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < n_f4; i += kThreads) {
+      const float4 z = ZLoad<T>::ld(a.z, zt + i);
+      const uint32_t byte = s_bytes[i >> 1];
+      const uint32_t ksn = (i & 1u) ? byte : (byte >> 4);
+      const uint32_t d = (quantise_nibble(z, thr) ^ ksn) & 0xFu;   // decrypted bits of 4 positions
+      if constexpr (kPow2) {
+        packed += (d * 0x00204081u) & 0x01010101u;                 // bit k -> byte lane k
+      } else {
+        const uint32_t pos = (uint32_t)((tile_base + 4 * (int64_t)i) % a.msg_bits);
+        if (d & 8u) atomicAdd(&s_cnt[pos + 0], 1u);
+        if (d & 4u) atomicAdd(&s_cnt[pos + 1], 1u);
+        if (d & 2u) atomicAdd(&s_cnt[pos + 2], 1u);
+        if (d & 1u) atomicAdd(&s_cnt[pos + 3], 1u);
+      }
+    }
+    if constexpr (kPow2) {
+      iters_since_spill += kTileF4 / kThreads;                     // 16 iterations per tile
+      if (iters_since_spill > 255 - kTileF4 / kThreads) {          // byte lanes would overflow next tile
+        c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
+        packed = 0; iters_since_spill = 0;
+      }
+    }
+  }
+  if constexpr (kPow2) {
+    c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
+    const uint32_t pos = (4u * threadIdx.x) & (a.msg_bits - 1u);
+    atomicAdd(&s_cnt[pos + 0], c3);            // byte lane 3 = nibble bit 3 = element 0
+    atomicAdd(&s_cnt[pos + 1], c2);
+    atomicAdd(&s_cnt[pos + 2], c1);
+    atomicAdd(&s_cnt[pos + 3], c0);
+  }
+  __syncthreads();
+
+  // majority vote, pack MSB-first, score against the reference message
+  const uint8_t* ref = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
+  int my_matched = 0;
+  for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) {   // msg_bits % 32 == 0: whole warps
+    const uint32_t cnt = s_cnt[p];
+    if (a.counts) a.counts[latent * a.msg_bits + p] = (uint16_t)cnt;
+    const bool bit = 2u * cnt > a.copies;                            // count_1 > len(segments)/2
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);         // lane l = position 32w + l
+    // position l of the word -> byte l>>3, bit 7-(l&7): reverse all bits, then swap bytes back
+    const uint32_t word = __byte_perm(__brev(ballot), 0u, 0x0123);
+    if ((threadIdx.x & 31) == 0) {
+      reinterpret_cast<uint32_t*>(a.msg_out + latent * (int64_t)(a.msg_bits >> 3))[p >> 5] = word;
+      if (ref) my_matched += __popc(~(word ^ __ldg(reinterpret_cast<const uint32_t*>(ref) + (p >> 5))));
+    }
+  }
+  if (ref) {
+    if ((threadIdx.x & 31) == 0 && my_matched) atomicAdd(&s_matched, my_matched);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int m = s_matched;
+      if (a.matched) a.matched[latent] = m;
+      if (a.counters) {
+        atomicAdd(&a.counters[GSWM_CTR_MATCHED_BITS], (unsigned long long)m);
+        atomicAdd(&a.counters[GSWM_CTR_EXACT_MSGS], (unsigned long long)(m == (int)a.msg_bits));
+      }
+    }
+  }
+  if (threadIdx.x == 0 && a.counters) {
+    atomicAdd(&a.counters[GSWM_CTR_TOTAL_BITS], (unsigned long long)a.msg_bits);
+    atomicAdd(&a.counters[GSWM_CTR_TOTAL_MSGS], 1ull);
+  }
+}
+
+// Test hook: evaluate the fp32 bucket quantile on caller-supplied raw words (exhaustive accuracy test).
+__global__ void __launch_bounds__(kThreads)
+debug_quantile_kernel(const uint32_t* __restrict__ w, int64_t n, uint32_t bucket_bit, int use_vec4, float* __restrict__ out) {
+  const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+  if (i >= n) return;
+  const uint32_t flip = bucket_bit ? 0u : 0xFFFFFFFFu;
+  const uint4 r = *reinterpret_cast<const uint4*>(w + i);
+  float4 z;
+  if (use_vec4) {
+    z = bucket_quantile4_f32(r, flip, flip, flip, flip);
+  } else {
+    z = make_float4(bucket_quantile_f32(r.x, flip), bucket_quantile_f32(r.y, flip), bucket_quantile_f32(r.z, flip),
+                    bucket_quantile_f32(r.w, flip));
+  }
+  *reinterpret_cast<float4*>(out + i) = z;
+}
+
+__global__ void __launch_bounds__(kThreads)
+debug_ppf64_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < n) out[i] = norm_ppf_f64(p[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the device entry points
+// ------------------------------------------------------------------------------------------------
+static int check_job(const gswm_job* job, bool for_extract) {
+  if (!job || !job->d_keys || !job->d_nonces) return GSWM_E_NULL;
+  if (!for_extract && !job->d_msgs) return GSWM_E_NULL;
+  if ((reinterpret_cast<uintptr_t>(job->d_keys) | reinterpret_cast<uintptr_t>(job->d_nonces) |
+       reinterpret_cast<uintptr_t>(job->d_msgs)) & 3u) return GSWM_E_ALIGN;   // read as 32-bit words
+  if (job->n_latents < 0 || job->n_elems <= 0 || (job->n_elems % 512) != 0) return GSWM_E_SHAPE;
+  if (job->msg_bits <= 0 || (job->msg_bits % 32) != 0 || job->msg_bits > job->n_elems) return GSWM_E_MSGLEN;
+  if (for_extract && (job->n_elems % job->msg_bits) != 0) return GSWM_E_MSGLEN;
+  if (job->n_elems > ((int64_t)1 << 31)) return GSWM_E_RANGE;
+  const int64_t tiles = (job->n_elems + kTileElems - 1) / kTileElems;
+  if (job->n_latents * tiles > 0x7FFFFFFFll) return GSWM_E_RANGE;
+  return GSWM_OK;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int launch_table(const gswm_job* job, bool with_msg, void* d_workspace, cudaStream_t st) {
+  if (!d_workspace) return GSWM_E_WORKSPACE;
+  if (!aligned16(d_workspace)) return GSWM_E_ALIGN;
+  const uint32_t blocks = (uint32_t)(job->n_elems / 512);
+  const uint32_t msg_words = (uint32_t)job->msg_bits / 32;
+  const uint32_t tiled_words = (uint32_t)(job->n_elems / job->msg_bits) * msg_words;
+  chacha20_keystream_kernel<<<(blocks + kThreads - 1) / kThreads, kThreads, 0, st>>>(
+      job->d_keys, job->d_nonces, with_msg ? job->d_msgs : nullptr, 1, blocks, msg_words, tiled_words, 0,
+      reinterpret_cast<uint32_t*>(d_workspace));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+static EmbedArgs make_embed_args(const gswm_job* job, void* d_workspace) {
+  EmbedArgs a{};
+  a.keys = job->d_keys;
+  a.nonces = job->d_nonces;
+  a.msgs = job->d_msgs;
+  a.table = reinterpret_cast<const uint32_t*>(d_workspace);
+  a.n_elems = job->n_elems;
+  a.tiles_per_latent = (uint32_t)((job->n_elems + kTileElems - 1) / kTileElems);
+  a.msg_words = (uint32_t)job->msg_bits / 32;
+  a.tiled_words = (uint32_t)(job->n_elems / job->msg_bits) * a.msg_words;
+  a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
+  return a;
+}
+
+template <typename T>
+static void launch_extract(const ExtractArgs& a, bool per_latent, bool pow2, unsigned grid, size_t smem, cudaStream_t st) {
+  if (per_latent) {
+    if (pow2) extract_kernel<T, true, true><<<grid, kThreads, smem, st>>>(a);
+    else extract_kernel<T, true, false><<<grid, kThreads, smem, st>>>(a);
+  } else {
+    if (pow2) extract_kernel<T, false, true><<<grid, kThreads, smem, st>>>(a);
+    else extract_kernel<T, false, false><<<grid, kThreads, smem, st>>>(a);
+  }
+}
+
+}  // namespace gswm
+
+using namespace gswm;
+
+extern "C" {
+
+int gswm_abi_version(void) { return GSWM_ABI_VERSION; }
+
+const char* gswm_strerror(int code) {
+  switch (code) {
+    case GSWM_OK: return "success";
+    case GSWM_E_NULL: return "gswm: a required pointer is NULL";
+    case GSWM_E_SHAPE: return "gswm: n_elems must be a positive multiple of 512 and n_latents >= 0";
+    case GSWM_E_MSGLEN: return "gswm: msg_bits must be a positive multiple of 32, <= n_elems (and divide it for extract)";
+    case GSWM_E_DTYPE: return "gswm: unknown element type";
+    case GSWM_E_RANGE: return "gswm: size out of range";
+    case GSWM_E_WORKSPACE: return "gswm: shared-key job needs a workspace of gswm_workspace_bytes()";
+    case GSWM_E_ALIGN: return "gswm: device pointer not 16-byte aligned";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gswm: unknown error";
+  }
+}
+
+int gswm_debug_bucket_quantile(const uint32_t* d_words, int64_t n, int32_t bucket_bit, int32_t use_vec4,
+                               float* d_out, void* stream) {
+  if (!d_words || !d_out) return GSWM_E_NULL;
+  if (n < 0 || (n % 4) != 0) return GSWM_E_SHAPE;
+  if (!aligned16(d_words) || !aligned16(d_out)) return GSWM_E_ALIGN;
+  if (n == 0) return GSWM_OK;
+  const int64_t grid = (n / 4 + kThreads - 1) / kThreads;
+  debug_quantile_kernel<<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(d_words, n, bucket_bit ? 1u : 0u,
+                                                                               use_vec4, d_out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int gswm_debug_norm_ppf(const double* d_p, int64_t n, double* d_out, void* stream) {
+  if (!d_p || !d_out) return GSWM_E_NULL;
+  if (n <= 0) return n == 0 ? GSWM_OK : GSWM_E_SHAPE;
+  debug_ppf64_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(d_p, n, d_out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int64_t gswm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t gswm_workspace_bytes(const gswm_job* job) {
+  if (!job || job->per_latent || job->n_elems <= 0) return 0;
+  return (size_t)(job->n_elems / 8);
+}
+
+int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int64_t n_streams,
+                            int64_t n_bytes_each, uint8_t* d_out, void* stream) {
+  if (!d_keys || !d_nonces || !d_out) return GSWM_E_NULL;
+  if (n_streams < 0 || n_bytes_each <= 0 || (n_bytes_each % 64) != 0) return GSWM_E_SHAPE;
+  if (!aligned16(d_out)) return GSWM_E_ALIGN;
+  const int64_t blocks_each = n_bytes_each / 64;
+  if (blocks_each > 0xFFFFFFFFll) return GSWM_E_RANGE;
+  const int64_t total = n_streams * blocks_each;
+  if (total == 0) return GSWM_OK;
+  const int64_t grid = (total + kThreads - 1) / kThreads;
+  if (grid > 0x7FFFFFFFll) return GSWM_E_RANGE;
+  chacha20_keystream_kernel<<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(
+      d_keys, d_nonces, nullptr, n_streams, (uint32_t)blocks_each, 0, 0, 0, reinterpret_cast<uint32_t*>(d_out));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent, float* d_out,
+               void* d_workspace, void* stream) {
+  int rc = check_job(job, false);
+  if (rc) return rc;
+  if (!d_out) return GSWM_E_NULL;
+  if (!aligned16(d_out)) return GSWM_E_ALIGN;
+  if (job->n_latents == 0) return GSWM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!job->per_latent && (rc = launch_table(job, true, d_workspace, st))) return rc;
+  EmbedArgs a = make_embed_args(job, d_workspace);
+  a.out = d_out;
+  a.first_latent = first_latent;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.off_lo = (uint32_t)offset; a.off_hi = (uint32_t)(offset >> 32);
+  const unsigned grid = (unsigned)(job->n_latents * a.tiles_per_latent);
+  if (job->per_latent) embed_kernel<true><<<grid, kThreads, 0, st>>>(a);
+  else embed_kernel<false><<<grid, kThreads, 0, st>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_latent, void* d_out,
+                        int32_t out_dtype, void* d_workspace, void* stream) {
+  int rc = check_job(job, false);
+  if (rc) return rc;
+  if (!d_out || !d_u) return GSWM_E_NULL;
+  if (out_dtype != GSWM_F32 && out_dtype != GSWM_F64) return GSWM_E_DTYPE;
+  if (job->n_latents == 0) return GSWM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!job->per_latent && (rc = launch_table(job, true, d_workspace, st))) return rc;
+  EmbedArgs a = make_embed_args(job, d_workspace);
+  const unsigned grid = (unsigned)(job->n_latents * a.tiles_per_latent);
+  const int upl = u_per_latent ? 1 : 0;
+  if (out_dtype == GSWM_F32) {
+    if (job->per_latent) embed_injected_kernel<true, float><<<grid, kThreads, 0, st>>>(a, d_u, upl, (float*)d_out);
+    else embed_injected_kernel<false, float><<<grid, kThreads, 0, st>>>(a, d_u, upl, (float*)d_out);
+  } else {
+    if (job->per_latent) embed_injected_kernel<true, double><<<grid, kThreads, 0, st>>>(a, d_u, upl, (double*)d_out);
+    else embed_injected_kernel<false, double><<<grid, kThreads, 0, st>>>(a, d_u, upl, (double*)d_out);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t* d_msg_out, uint16_t* d_counts,
+                 int32_t* d_matched, int64_t* d_counters, void* d_workspace, void* stream) {
+  int rc = check_job(job, true);
+  if (rc) return rc;
+  if (!d_z || !d_msg_out) return GSWM_E_NULL;
+  if (z_dtype != GSWM_F32 && z_dtype != GSWM_F16 && z_dtype != GSWM_BF16) return GSWM_E_DTYPE;
+  if (!aligned16(d_z) || (reinterpret_cast<uintptr_t>(d_msg_out) & 3u)) return GSWM_E_ALIGN;
+  const int64_t copies = job->n_elems / job->msg_bits;
+  if (d_counts && copies > 65535) return GSWM_E_RANGE;
+  if (job->msg_bits > 8192) return GSWM_E_RANGE;
+  if (job->n_latents == 0) return GSWM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!job->per_latent && (rc = launch_table(job, false, d_workspace, st))) return rc;
+  ExtractArgs a{};
+  a.keys = job->d_keys; a.nonces = job->d_nonces; a.msgs = job->d_msgs;
+  a.table = reinterpret_cast<const uint32_t*>(d_workspace);
+  a.z = d_z; a.msg_out = d_msg_out; a.counts = d_counts; a.matched = d_matched;
+  a.counters = reinterpret_cast<unsigned long long*>(d_counters);
+  a.n_elems = job->n_elems;
+  a.tiles_per_latent = (uint32_t)((job->n_elems + kTileElems - 1) / kTileElems);
+  a.msg_bits = (uint32_t)job->msg_bits;
+  a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
+  a.copies = (uint32_t)copies;
+  const bool pow2 = (1024 % job->msg_bits) == 0;
+  const size_t smem = (size_t)(kTileWords + job->msg_bits) * sizeof(uint32_t);
+  const unsigned grid = (unsigned)job->n_latents;
+  if (z_dtype == GSWM_F32) launch_extract<float>(a, job->per_latent != 0, pow2, grid, smem, st);
+  else if (z_dtype == GSWM_F16) launch_extract<__half>(a, job->per_latent != 0, pow2, grid, smem, st);
+  else launch_extract<__nv_bfloat16>(a, job->per_latent != 0, pow2, grid, smem, st);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+"""ctypes binding of libgswm.so (C ABI declared in include/gswm.h).
+
+The library is built in-tree by :func:`build` (plain ``nvcc -gencode arch=compute_100a,code=sm_100a``;
+no torch headers) and must exist for anything in this package to work: there is no CPU or PyTorch
+fallback, a missing or unloadable library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
+_INCLUDE = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include")
+LIB_PATH = os.path.join(_HERE, "libgswm.so")
+SOURCES = ["gswm_kernels.cu", "gswm_pipe.cu"]
+
+GSWM_F32, GSWM_F16, GSWM_BF16, GSWM_F64 = 0, 1, 2, 3
+CTR_MATCHED_BITS, CTR_TOTAL_BITS, CTR_EXACT_MSGS, CTR_TOTAL_MSGS, N_COUNTERS = 0, 1, 2, 3, 4
+
+EXPORTS = [
+    "gswm_abi_version", "gswm_strerror", "gswm_workspace_bytes", "gswm_chacha20_keystream", "gswm_embed",
+    "gswm_embed_injected", "gswm_extract", "gswm_pipe_create", "gswm_pipe_destroy", "gswm_pipe_embed",
+    "gswm_pipe_embed_injected", "gswm_pipe_extract", "gswm_launch_count", "gswm_debug_bucket_quantile",
+    "gswm_debug_norm_ppf",
+]
+
+
+class GswmError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"{what} failed: {code} ({strerror(code)})")
+        self.code = code
+
+
+class Job(C.Structure):
+    """struct gswm_job / gswm_host_job (identical layout)."""
+    _fields_ = [("n_latents", C.c_int64), ("n_elems", C.c_int64), ("msg_bits", C.c_int32),
+                ("per_latent", C.c_int32), ("keys", C.c_void_p), ("nonces", C.c_void_p), ("msgs", C.c_void_p)]
+
+
+def nvcc_command(out: str = LIB_PATH, extra=()):
+    srcs = [os.path.join(_CSRC, s) for s in SOURCES]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", f"-I{_INCLUDE}", *extra, "-o", out, *srcs]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libgswm.so for sm_100a (cross-compiles without a GPU).  Returns its path."""
+    srcs = [os.path.join(_CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".inc"))]
+    deps.append(os.path.join(_INCLUDE, "gswm.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = nvcc_command(extra=("-Xptxas", "-v") if verbose else ())
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load libgswm.so once; raise loudly when it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not built -- run `python __graft_entry__.py build` "
+                              "(gswm has no CPU / PyTorch fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+        JP = C.POINTER(Job)
+        L.gswm_abi_version.restype = C.c_int
+        L.gswm_strerror.restype = C.c_char_p
+        L.gswm_strerror.argtypes = [C.c_int]
+        L.gswm_workspace_bytes.restype = C.c_size_t
+        L.gswm_workspace_bytes.argtypes = [JP]
+        L.gswm_chacha20_keystream.argtypes = [vp, vp, i64, i64, vp, vp]
+        L.gswm_embed.argtypes = [JP, u64, u64, i64, vp, vp, vp]
+        L.gswm_embed_injected.argtypes = [JP, vp, i32, vp, i32, vp, vp]
+        L.gswm_extract.argtypes = [JP, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.gswm_pipe_create.argtypes = [C.POINTER(vp), C.c_int, i64, i64]
+        L.gswm_pipe_destroy.argtypes = [vp]
+        L.gswm_pipe_destroy.restype = None
+        L.gswm_pipe_embed.argtypes = [vp, JP, u64, u64, i64, vp]
+        L.gswm_pipe_embed_injected.argtypes = [vp, JP, vp, i32, vp, i32]
+        L.gswm_pipe_extract.argtypes = [vp, JP, vp, i32, vp, vp, vp, vp]
+        L.gswm_launch_count.restype = i64
+        L.gswm_debug_bucket_quantile.argtypes = [vp, i64, i32, i32, vp, vp]
+        L.gswm_debug_bucket_quantile.restype = C.c_int
+        L.gswm_debug_norm_ppf.argtypes = [vp, i64, vp, vp]
+        L.gswm_debug_norm_ppf.restype = C.c_int
+        for name in ("gswm_chacha20_keystream", "gswm_embed", "gswm_embed_injected", "gswm_extract",
+                     "gswm_pipe_create", "gswm_pipe_embed", "gswm_pipe_embed_injected", "gswm_pipe_extract"):
+            getattr(L, name).restype = C.c_int
+        if L.gswm_abi_version() != 1:
+            raise ImportError("libgswm.so ABI version mismatch")
+        _lib = L
+        return L
+
+
+def strerror(code: int) -> str:
+    return lib().gswm_strerror(int(code)).decode()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise GswmError(code, what)
+
+
+def launch_count() -> int:
+    return int(lib().gswm_launch_count())

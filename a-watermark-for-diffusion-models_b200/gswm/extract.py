@@ -1,0 +1,65 @@
+"""Drop-in for the codec half of the reference's ``extract.py`` (extract.py:72-110): same names,
+arguments and return values; the DDIM-inversion / CLI half (extract.py:31-70, 112-211) stays
+upstream and keeps calling these two functions.
+
+    from gswm.extract import recover_exactracted_message, calculate_bit_accuracy
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import codec
+
+# int(norm.cdf(z) * 2) is 1 from this float64 value upwards and 2 (reference crashes) from the second
+_CDF_HALF = -6.957291061679417e-17
+_CDF_ONE = 8.292361075813597
+
+
+def _as_tensor(reversed_latents) -> torch.Tensor:
+    if isinstance(reversed_latents, torch.Tensor):
+        return reversed_latents.detach()
+    return torch.from_numpy(np.ascontiguousarray(reversed_latents))
+
+
+def recover_exactracted_message(reversed_latents, args) -> str:
+    """extract.py:72-101.  ``reversed_latents``: the inverted latent, any shape that flattens (C
+    order, as np.nditer walks it) to the embedded element order -- normally a (1, 4, h, w) fp16 CPU
+    tensor (extract.py:48,70).  ``args`` carries ``key``, ``nonce`` (bytes), ``l`` and
+    ``message_length``.  Returns the '0'/'1' string of length message_length.
+
+    Raises ValueError where the reference does: NaN input (int(nan)) and any z with
+    norm.cdf(z) * 2 rounding to 2 (z >= 8.2924, +inf), whose digit '2' breaks int(..., 2) at
+    extract.py:86.
+    """
+    if int(args.l) != 1:
+        # extract.py:84-86 emits digits >= 2 into a base-2 parse for l > 1: non-functional upstream
+        raise ValueError("invalid literal for int() with base 2 (window size l must be 1)")
+    z = _as_tensor(reversed_latents).reshape(1, -1)
+    if torch.isnan(z).any():
+        raise ValueError("cannot convert float NaN to integer")
+    if (z >= _CDF_ONE).any():
+        raise ValueError("invalid literal for int() with base 2: cdf(z) * 2 == 2")
+    if z.dtype == torch.float64:
+        # keep the float64 threshold exact: quantise on the host side of the copy, ship +-1
+        z = torch.where(z >= _CDF_HALF, 1.0, -1.0).to(torch.float32)
+    elif z.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        z = z.to(torch.float32)
+    msg_bits = int(args.message_length)
+    km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)
+    if z.numel() % msg_bits:
+        # extract.py:94,98: the short last segment is indexed past its end
+        raise IndexError("string index out of range")
+    dev = z.device if z.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    res = codec.extract_batch(z.to(dev), km)
+    return res.bit_strings()[0]
+
+
+def calculate_bit_accuracy(original_message_hex, extracted_message_bin):
+    """extract.py:103-110 (host string arithmetic, O(message length))."""
+    width = 4 * len(original_message_hex)                       # zero-padded: 4 bits per hex digit
+    reference_bits = format(int(original_message_hex, 16), f"0{width}b")
+    n = min(len(reference_bits), len(extracted_message_bin))      # silently truncates to the shorter one
+    reference_bits = reference_bits[:n]
+    agree = sum(a == b for a, b in zip(reference_bits, extracted_message_bin[:n]))
+    return reference_bits, agree / n

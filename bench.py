@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- embed+extract throughput of the Gaussian-Shading codec hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, libgswm.so)
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU arm: the reference's algorithm on host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # N > 1, one rank per GPU
+
+One "step" = one pass of the hot path over one batch: embed B latents (K2) and extract B latents
+(K3) -- BASELINE config[1] + config[2]: B = 4096 SD-2.1 latents (4x64x64), 256-bit message, shared
+default key/nonce, message 'lthero', extraction input = embedded latents + sigma*N(0,1), sigma = 0.325.
+`value` = pairs (latent embedded AND latent decoded) per second with inputs resident in HBM;
+`e2e` = the same through the host-buffer C ABI (gswm_pipe_*), PCIe copies inside the timed region.
+Weak scaling: every rank processes its own B latents (global latent index = rank * B + b).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "a-watermark-for-diffusion-models_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "embed+extract latents/s (4x64x64, 256-bit); bit-exact decode"
+UNIT = "latents/s"
+SHAPES = {"sd21": (4, 64, 64), "sdxl": (4, 128, 128)}
+SIGMA = 0.325
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="latents per GPU per step")
+    ap.add_argument("--shape", default="sd21", choices=sorted(SHAPES))
+    ap.add_argument("--msg-bits", type=int, default=256)
+    ap.add_argument("--per-latent-keys", action="store_true", help="BASELINE config[4]: distinct key/nonce/message per latent")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    c, h, w = SHAPES[args.shape]
+    keys = "per-latent key/nonce/message" if args.per_latent_keys else "shared default key/nonce, message 'lthero'"
+    return (f"BASELINE configs[1]+[2]: embed {args.batch} latents ({c}x{h}x{w}, per-sample noise) + extract {args.batch} "
+            f"noisy latents (sigma={SIGMA}), {args.msg_bits}-bit message, {keys}")
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(job):
+    """One worker: `pairs` embed+extract pairs of the oracle port (numpy/scipy/cryptography), returns seconds."""
+    from oracle import gs_oracle as O
+    pairs, n, msg_bits, seed = job
+    key, nonce = bytes.fromhex(O.DEFAULT_KEY_HEX), bytes.fromhex(O.DEFAULT_NONCE_HEX)
+    rs = np.random.RandomState(seed)
+    noise = np.float32(SIGMA) * rs.standard_normal(n).astype(np.float32)   # synthetic perturbation, made once
+    ks = O.chacha20_keystream_lib                                           # the reference's own OpenSSL call
+    ok = 0
+    t0 = time.perf_counter()
+    for _ in range(pairs):
+        u = rs.uniform(size=n)                                             # gs_insert.py:62
+        z = O.embed("lthero", key, nonce, u, msg_bits, keystream=ks).astype(np.float32)   # gs_insert.py:23-66 + .float()
+        bits = O.recover_message_bits(z + noise, key, nonce, msg_bits, keystream=ks)       # extract.py:72-101
+        ok += int(O.bits_to_bytes(bits)[:6] == b"lthero")
+    return time.perf_counter() - t0, ok
+
+
+def cpu_pairs_per_second(n_elems, msg_bits, pairs_per_worker, cores):
+    """All `cores` workers run `pairs_per_worker` pairs concurrently; returns (pairs/s, total pairs, all decoded ok)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    jobs = [(pairs_per_worker, n_elems, msg_bits, 1000 + i) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = pairs_per_worker * cores
+    return total / wall, total, sum(r[1] for r in res) == total
+
+
+def calibrate_cpu(n_elems, msg_bits):
+    t, _ = _cpu_worker((4, n_elems, msg_bits, 1))
+    return t / 4
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = int(np.prod(SHAPES[args.shape]))
+    cores = len(os.sched_getaffinity(0))
+    per_pair = calibrate_cpu(n, args.msg_bits)
+    # each step: a bounded sample so that warmup + steps stays within ~2 minutes
+    budget_per_step = min(6.0, 100.0 / max(1, args.steps + args.warmup))
+    ppw = max(2, int(budget_per_step / per_pair))
+    for _ in range(args.warmup):
+        cpu_pairs_per_second(n, args.msg_bits, max(1, ppw // 4), cores)
+    t0 = time.perf_counter()
+    total = 0
+    ok = True
+    for _ in range(args.steps):
+        _, tp, o = cpu_pairs_per_second(n, args.msg_bits, ppw, cores)
+        total += tp
+        ok &= o
+    wall = time.perf_counter() - t0
+    value = total / wall
+    sample = f"{ppw * cores} embed+extract pairs per step ({ppw} per core x {cores} processes), vectorised numpy/scipy/cryptography port of the reference"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample, "decoded_ok": bool(ok)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch from the committed ncu capture, if profiles/ncu_traffic.json has it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import gswm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: gswm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gswm._lib.lib()
+
+    shape = SHAPES[args.shape]
+    n = int(np.prod(shape))
+    B, L = args.batch, args.msg_bits
+    first = rank * B                                   # global latent index of this rank's shard
+    if args.per_latent_keys:
+        rs = np.random.RandomState(2025)
+        allk = rs.bytes(32 * B * world); alln = rs.bytes(16 * B * world); allm = rs.bytes((L // 8) * B * world)
+        km = gswm.KeyMaterial.make(allk[32 * first:32 * (first + B)], alln[16 * first:16 * (first + B)],
+                                   allm[(L // 8) * first:(L // 8) * (first + B)], L)
+    else:
+        km = gswm.KeyMaterial.make(bytes.fromhex(gswm.DEFAULT_KEY_HEX), bytes.fromhex(gswm.DEFAULT_NONCE_HEX),
+                                   gswm.pad_message("lthero", L // 8), L)
+    seed = 0x5EED
+
+    # ---- resident inputs: key material on device, noisy latents for the extract side -------------------------
+    from gswm.codec import _DeviceJob
+    import ctypes as C
+    lib = gswm._lib.lib()
+    dj = _DeviceJob(km, B, n, dev)
+    z = torch.empty((B, *shape), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+    gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
+    g = torch.Generator(dev).manual_seed(99 + rank)
+    z_noisy = z + SIGMA * torch.randn(z.shape, device=dev, generator=g)
+    msgs = torch.empty((B, L // 8), dtype=torch.uint8, device=dev)
+    matched = torch.empty((B,), dtype=torch.int32, device=dev)
+    counters = torch.zeros((4,), dtype=torch.int64, device=dev)
+    ws2 = torch.empty_like(dj.workspace) if dj.workspace is not None else None
+    ws2p = ws2.data_ptr() if ws2 is not None else None
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
+        if ev:
+            ev[1].record(stream)
+        counters.zero_()
+        gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
+                                         counters.data_ptr(), ws2p, sp), "gswm_extract")
+        if ev:
+            ev[2].record(stream)
+        if world > 1:
+            dist.all_reduce(counters)                  # the only collective: 32 bytes of bit-match counters
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    launches0 = gswm.launch_count()
+    barrier()
+    t_begin.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record(stream)
+    barrier()
+    launches = gswm.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_begin.elapsed_time(t_end)
+    embed_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    extract_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    final = counters.cpu().numpy().tolist()
+    exact = final[2] == final[3] == B * world          # every message decodes exactly at sigma = 0.325
+
+    tm = torch.tensor([total_ms, embed_ms, extract_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, embed_ms, extract_ms = tm.cpu().tolist()
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI pipe (PCIe inside the timed region) -------------------------------
+    pipe = gswm.HostPipe(local, max_elems=n, chunk_latents=256)
+    h_out = torch.empty((B, *shape), dtype=torch.float32).pin_memory()
+    h_in = z_noisy.cpu().pin_memory()
+    e2e_steps = max(1, args.e2e_steps)
+
+    def e2e_step():
+        pipe.embed(h_out, km, seed, 0, first)
+        return pipe.extract(h_in, km)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _, _, _, h_cnt = e2e_step()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = B * world * e2e_steps / e2e_s
+    e2e_ok = int(h_cnt[2]) == B
+    key_bytes = km.keys.nbytes + km.nonces.nbytes + (km.msgs.nbytes if km.msgs is not None else 0)
+    chunks = (B + 255) // 256
+    h2d = B * n * 4 + (key_bytes * (1 if km.per_latent else chunks)) * 2
+    d2h = B * n * 4 + B * (L // 8) + B * 4 + 32
+    pipe.close()
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak_gbs()
+    lat_bytes = B * n * 4
+    k_embed = {"ms": embed_ms, "GBps": lat_bytes / (embed_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
+    k_extract = {"ms": extract_ms, "GBps": lat_bytes / (extract_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
+    dom_name, dom = ("embed_kernel", k_embed) if embed_ms >= extract_ms else ("extract_kernel", k_extract)
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["GBps"] / peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
+                "kernels": {"embed_kernel": dict(k_embed, frac=k_embed["GBps"] / peak),
+                            "extract_kernel": dict(k_extract, frac=k_extract["GBps"] / peak)}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        per_pair = calibrate_cpu(n, L)
+        ppw = max(2, int(args.cpu_seconds / per_pair))
+        v, tp, ok = cpu_pairs_per_second(n, L, ppw, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{tp} embed+extract pairs ({ppw} per core x {cores} processes) of the same latent shape, vectorised "
+                         f"numpy/scipy/cryptography port of the reference (oracle/gs_oracle.py); decoded_ok={ok}"}
+
+    c, h, w = shape
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "latents_per_gpu": B, "latent_shape": [c, h, w], "msg_bits": L,
+                   "l2": "inputs larger than L2 (2 x 268 MB streamed per step vs 126 MB L2)" if lat_bytes > 126e6 else
+                         "WARNING: working set fits L2", "timing": "CUDA events on the launch stream, max over ranks",
+                   "decode_exact": bool(exact), "counters": final},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "decode_exact": bool(e2e_ok),
+                "path": "gswm_pipe_embed -> pinned host fp32; pinned host fp32 -> gswm_pipe_extract (256-latent chunks, 2 slots)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

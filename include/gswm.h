@@ -1,0 +1,182 @@
+/*
+ * gswm.h -- C ABI of libgswm.so: the Gaussian-Shading watermark codec hot path on B200 (sm_100a).
+ *
+ * The reference (lthero-big/A-watermark-for-Diffusion-Models) has no FFI: its "API" is a handful of
+ * Python functions built from three third-party calls.  Each entry point below names the reference
+ * statement(s) it replaces (file:line relative to the reference repository).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream).
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *   - the device entry points never allocate, free or synchronise: work is enqueued on `stream` and
+ *     the call returns; outputs are fully overwritten.  Only gswm_pipe_* (host-buffer convenience
+ *     layer) owns device memory, allocated once in gswm_pipe_create.
+ *   - return value: 0 = success; negative = GSWM_E_* argument error; positive = cudaError_t.
+ *   - bit order: latent element e of a latent maps to keystream byte e>>3, bit 7-(e&7)
+ *     (gs_insert.py:49 `format(byte,'08b')`, extract.py:86).
+ *   - a latent is the C-order flattening of (4, H/8, W/8) (gs_insert.py:56,65); n_elems = 4*(H/8)*(W/8).
+ */
+#ifndef GSWM_H_
+#define GSWM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSWM_ABI_VERSION 1
+
+enum {
+  GSWM_OK = 0,
+  GSWM_E_NULL = -1,        /* a required pointer is NULL */
+  GSWM_E_SHAPE = -2,       /* n_elems not a positive multiple of 512, or n_latents < 0 */
+  GSWM_E_MSGLEN = -3,      /* msg_bits not a positive multiple of 32, > n_elems, or (extract) not dividing n_elems */
+  GSWM_E_DTYPE = -4,       /* unknown element type code */
+  GSWM_E_RANGE = -5,       /* a size exceeds what the kernels index */
+  GSWM_E_WORKSPACE = -6,   /* shared-key job without a workspace of gswm_workspace_bytes() */
+  GSWM_E_ALIGN = -7        /* latent/workspace pointer not 16-byte aligned, or key/nonce/message not 4-byte aligned */
+};
+
+/* element type codes for latents */
+enum { GSWM_F32 = 0, GSWM_F16 = 1, GSWM_BF16 = 2, GSWM_F64 = 3 };
+
+/*
+ * One batch job: n_latents latents of n_elems elements each, msg_bits-bit messages.
+ *
+ *   per_latent == 0 : d_keys[32], d_nonces[16], d_msgs[msg_bits/8] are shared by the whole batch
+ *                     (the reference's usual case: one --key_hex/--nonce_hex/--message per run).
+ *   per_latent == 1 : d_keys[n][32], d_nonces[n][16], d_msgs[n][msg_bits/8], one row per latent.
+ *
+ * key/nonce are the bytes gs_insert.py:27-42 resolves from key_hex/nonce_hex; the message bytes are
+ * the padded/truncated `k` of gs_insert.py:9-20 (nodes.py:68-76, v1.5.2:29-47 for other framings).
+ * The message is tiled n_elems/msg_bits times; a remainder (msg_bits not dividing n_elems, embed only)
+ * carries plaintext zero, as nodes.py:79-87 does.
+ */
+typedef struct gswm_job {
+  int64_t n_latents;
+  int64_t n_elems;
+  int32_t msg_bits;
+  int32_t per_latent;
+  const uint8_t* d_keys;
+  const uint8_t* d_nonces;
+  const uint8_t* d_msgs;   /* extract: may be NULL (no reference message to score against) */
+} gswm_job;
+
+/* counters written by gswm_extract (int64 each) -- the buffer an all-reduce over ranks sums */
+enum {
+  GSWM_CTR_MATCHED_BITS = 0, /* sum over latents of decoded bits equal to the reference message */
+  GSWM_CTR_TOTAL_BITS = 1,   /* n_latents * msg_bits */
+  GSWM_CTR_EXACT_MSGS = 2,   /* latents whose decoded message equals the reference exactly */
+  GSWM_CTR_TOTAL_MSGS = 3,   /* n_latents */
+  GSWM_N_COUNTERS = 4
+};
+
+int gswm_abi_version(void);
+const char* gswm_strerror(int code);
+
+/* Bytes of device workspace a shared-key job needs (0 for per_latent jobs). */
+size_t gswm_workspace_bytes(const gswm_job* job);
+
+/*
+ * ChaCha20 keystream, original 64-bit-counter layout: state words 12,13 = LE64(nonce[0:8]) + block,
+ * words 14,15 = nonce[8:16] -- what `Cipher(algorithms.ChaCha20(key, nonce)).encryptor().update(zeros)`
+ * yields (gs_insert.py:45-47, nodes.py:101-103, extract.py:77-78,87).
+ * d_out[s][0:n_bytes_each] for s < n_streams; n_bytes_each must be a multiple of 64.
+ */
+int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int64_t n_streams,
+                            int64_t n_bytes_each, uint8_t* d_out, void* stream);
+
+/*
+ * Embed with the in-kernel counter-based uniform source -- replaces the whole of
+ * gs_insert.gs_watermark_init_noise's arithmetic (gs_insert.py:23-66; nodes.py:76-123) for a batch:
+ * tile message, XOR ChaCha20 keystream, one uniform per element, z = Phi^-1((u + y) / 2), fp32 store.
+ *
+ * The uniform of global element g = (first_latent + b) * n_elems + e is
+ *     u = ((w >> 9) + 0.5) * 2^-23,   w = word (g & 3) of Philox4x32-10(ctr = {g>>2, offset}, key = seed)
+ * so a batch sharded over ranks by first_latent produces the same latents as one big batch.
+ * d_out: [n_latents][n_elems] fp32, 16-byte aligned.  d_workspace: gswm_workspace_bytes(job).
+ */
+int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent,
+               float* d_out, void* d_workspace, void* stream);
+
+/*
+ * Embed with injected uniforms: d_u[n_latents][n_elems] float64 in [0,1) takes the place of
+ * np.random.uniform(0,1) / RandomState(seed).uniform(0,1) (gs_insert.py:62; nodes.py:114-117) and
+ * z = Phi^-1((u + y)/2) is evaluated in float64 (gs_insert.py:64).  u_per_latent == 0 reuses one
+ * row of uniforms for every latent.  out_dtype: GSWM_F32 (what every caller casts to, README.md:112)
+ * or GSWM_F64 (what gs_insert.py:75 returns).
+ */
+int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_latent, void* d_out,
+                        int32_t out_dtype, void* d_workspace, void* stream);
+
+/*
+ * Extract -- replaces extract.recover_exactracted_message (extract.py:72-101) and the counting half
+ * of calculate_bit_accuracy (extract.py:103-110) for a batch of inverted latents d_z
+ * [n_latents][n_elems] of type z_dtype (GSWM_F32 / GSWM_F16 / GSWM_BF16):
+ *   bit = int(norm.cdf(z)*2)  ==  (z >= -6.957291061679417e-17)       extract.py:82-84
+ *   decrypt with the keystream, count ones per message position over the n_elems/msg_bits copies,
+ *   strict majority (tie -> 0)                                         extract.py:86-99
+ * Outputs (each may be NULL except d_msg_out):
+ *   d_msg_out [n_latents][msg_bits/8]   decoded message, MSB-first bits (bytes of the '0'/'1' string)
+ *   d_counts  [n_latents][msg_bits] u16 count_1 per position (needs n_elems/msg_bits <= 65535)
+ *   d_matched [n_latents] i32           bits equal to job->d_msgs (the reference message), per latent
+ *   d_counters[GSWM_N_COUNTERS] i64     ACCUMULATED (caller zeroes); see GSWM_CTR_*
+ * d_matched / matched counters need job->d_msgs.
+ */
+int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t* d_msg_out,
+                 uint16_t* d_counts, int32_t* d_matched, int64_t* d_counters, void* d_workspace,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer layer: what a caller holding numpy / CPU-torch buffers uses (the reference builds its
+ * latents on the CPU and `.to(device)`s them, README.md:112; extract.py:70 hands back a CPU tensor).
+ * A pipe owns streams, pinned staging and device buffers sized for `max_latents_per_chunk` latents of
+ * `max_elems` elements; batches of any size are streamed through it in chunks with the H2D / kernel /
+ * D2H stages of consecutive chunks overlapped.  Host job fields (h_keys/h_nonces/h_msgs) follow the
+ * gswm_job rules but point to host memory.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gswm_pipe gswm_pipe;
+
+typedef struct gswm_host_job {
+  int64_t n_latents;
+  int64_t n_elems;
+  int32_t msg_bits;
+  int32_t per_latent;
+  const uint8_t* h_keys;
+  const uint8_t* h_nonces;
+  const uint8_t* h_msgs;
+} gswm_host_job;
+
+int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max_latents_per_chunk);
+void gswm_pipe_destroy(gswm_pipe* pipe);
+
+/* h_out [n_latents][n_elems] fp32 host memory (pinned memory gives full PCIe rate). Synchronous. */
+int gswm_pipe_embed(gswm_pipe* pipe, const gswm_host_job* job, uint64_t seed, uint64_t offset,
+                    int64_t first_latent, float* h_out);
+
+/* h_u [n_latents or 1][n_elems] float64, h_out fp32 or fp64 per out_dtype. Synchronous. */
+int gswm_pipe_embed_injected(gswm_pipe* pipe, const gswm_host_job* job, const double* h_u,
+                             int32_t u_per_latent, void* h_out, int32_t out_dtype);
+
+/* h_z [n_latents][n_elems] of z_dtype; outputs as gswm_extract but in host memory; h_counters[4]
+ * is OVERWRITTEN with this batch's totals. Synchronous. */
+int gswm_pipe_extract(gswm_pipe* pipe, const gswm_host_job* job, const void* h_z, int32_t z_dtype,
+                      uint8_t* h_msg_out, uint16_t* h_counts, int32_t* h_matched, int64_t* h_counters);
+
+/* Test hooks (used by tests/ only): the fp32 bucket quantile of gswm_embed on caller-supplied raw
+ * 32-bit words (u = ((w >> 9) + 0.5) * 2^-23, all elements in bucket `bucket_bit`; use_vec4 selects
+ * the 4-wide code path the embed kernel runs), and the fp64 Phi^-1 of gswm_embed_injected. */
+int gswm_debug_bucket_quantile(const uint32_t* d_words, int64_t n, int32_t bucket_bit, int32_t use_vec4,
+                               float* d_out, void* stream);
+int gswm_debug_norm_ppf(const double* d_p, int64_t n, double* d_out, void* stream);
+
+/* Number of kernels the library has launched in this process (all entry points); for bench.py. */
+int64_t gswm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSWM_H_ */

@@ -169,9 +169,12 @@ def resolve_key_nonce(key_hex: str, nonce_hex: str):
 # --------------------------------------------------------------------------
 # embed
 # --------------------------------------------------------------------------
-def bucket_bits(s_d: bytes, key: bytes, nonce16: bytes) -> np.ndarray:
-    """y bit per latent element: MSB-first bits of  s_d XOR keystream  (gs_insert.py:45-49,58-60)."""
-    ks = chacha20_keystream(key, nonce16, len(s_d))
+def bucket_bits(s_d: bytes, key: bytes, nonce16: bytes, keystream=chacha20_keystream) -> np.ndarray:
+    """y bit per latent element: MSB-first bits of  s_d XOR keystream  (gs_insert.py:45-49,58-60).
+
+    ``keystream`` selects the numpy restatement (default) or ``chacha20_keystream_lib`` (the reference's
+    own library call; used by bench.py's CPU baseline so the baseline is not slowed by numpy ChaCha)."""
+    ks = keystream(key, nonce16, len(s_d))
     m = np.frombuffer(s_d, dtype=np.uint8) ^ ks
     return np.unpackbits(m)  # default bitorder='big' == format(byte, '08b')
 
@@ -185,11 +188,11 @@ def embed_from_uniform(y: np.ndarray, u: np.ndarray) -> np.ndarray:
 
 
 def embed(message, key: bytes, nonce16: bytes, u: np.ndarray, l_bits: int = 256,
-          use_repeat: bool = False) -> np.ndarray:
+          use_repeat: bool = False, keystream=chacha20_keystream) -> np.ndarray:
     """Whole embed for one latent; ``u`` is the flat float64 uniform stream (length N)."""
     n = int(np.asarray(u).size)
     _, s_d = frame_message(message, n, l_bits, use_repeat)
-    y = bucket_bits(s_d, key, nonce16)
+    y = bucket_bits(s_d, key, nonce16, keystream)
     return embed_from_uniform(y, np.asarray(u).reshape(-1))
 
 
@@ -275,21 +278,22 @@ def quantise(z: np.ndarray) -> np.ndarray:
     return q.astype(np.uint8)
 
 
-def vote_counts(z: np.ndarray, key: bytes, nonce16: bytes, l_bits: int) -> np.ndarray:
+def vote_counts(z: np.ndarray, key: bytes, nonce16: bytes, l_bits: int, keystream=chacha20_keystream) -> np.ndarray:
     """count_1 per message position (extract.py:86-98): uint32 [L]."""
     bits = quantise(z)
     n = bits.size
     if n % 8 or n % l_bits:
         raise ValueError("latent size must be a multiple of 8 and of the message length")
     m = np.packbits(bits)
-    s_d = m ^ chacha20_keystream(key, nonce16, m.size)
+    s_d = m ^ keystream(key, nonce16, m.size)
     all_bits = np.unpackbits(s_d)
     return all_bits.reshape(-1, l_bits).sum(axis=0).astype(np.uint32)
 
 
-def recover_message_bits(z: np.ndarray, key: bytes, nonce16: bytes, l_bits: int) -> np.ndarray:
+def recover_message_bits(z: np.ndarray, key: bytes, nonce16: bytes, l_bits: int,
+                         keystream=chacha20_keystream) -> np.ndarray:
     """extract.py:97-99: strict majority over the R = N / L copies; uint8 [L]."""
-    counts = vote_counts(z, key, nonce16, l_bits)
+    counts = vote_counts(z, key, nonce16, l_bits, keystream)
     r = np.asarray(z).size // l_bits
     return (counts > r / 2).astype(np.uint8)
 

@@ -1,0 +1,397 @@
+"""Parity of the CUDA path (libgswm.so through its C ABI) against the oracle and the golden vectors.
+
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+Bars (BASELINE.json north_star): keystream, bucket membership (sign), vote counts, decoded messages and
+bit counts BIT-EXACT; latents within 1e-6 relative of scipy's float64 norm.ppf.
+"""
+import ctypes as C
+import hashlib
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6   # north_star: latents within 1e-6 relative of scipy's float64 norm.ppf
+KEY = bytes.fromhex(O.DEFAULT_KEY_HEX)
+NONCE = bytes.fromhex(O.DEFAULT_NONCE_HEX)
+
+
+@pytest.fixture(scope="module")
+def gswm(cuda_device):
+    import gswm as g
+    g._lib.lib()   # raises if the extension is missing: no fallback
+    return g
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.abs(got - ref) / np.abs(ref)
+    e[(ref == 0) & (got == 0)] = 0.0
+    e[np.isinf(ref) & (got == ref)] = 0.0
+    return e
+
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------------------------ K1 ChaCha20
+def test_chacha20_golden(gswm, golden):
+    for c in golden["chacha20"]:
+        ks = gswm.chacha20_keystream(bytes.fromhex(c["key"]), bytes.fromhex(c["nonce"]), c["nbytes"]).cpu().numpy()[0]
+        s = ks.tobytes()
+        assert s[:64].hex() == c["first64"], c["name"]
+        assert s[-64:].hex() == c["last64"], c["name"]
+        assert hashlib.sha256(s).hexdigest() == c["sha256"], c["name"]
+
+
+def test_chacha20_many_keys_vs_oracle(gswm):
+    rs = np.random.RandomState(2025)
+    n = 300
+    keys = np.frombuffer(rs.bytes(32 * n), np.uint8).reshape(n, 32).copy()
+    nonces = np.frombuffer(rs.bytes(16 * n), np.uint8).reshape(n, 16).copy()
+    nonces[0, :8] = 0xFF                       # 64-bit counter wraps to zero
+    nonces[1, :4] = 0xFF; nonces[1, 4:8] = 0    # carry into word 13
+    got = gswm.chacha20_keystream(keys, nonces, 2048).cpu().numpy()
+    for i in range(n):
+        ref = O.chacha20_keystream(keys[i].tobytes(), nonces[i].tobytes(), 2048)
+        assert np.array_equal(got[i], ref), i
+    lib_ref = O.chacha20_keystream_lib(keys[1].tobytes(), nonces[1].tobytes(), 2048)
+    assert np.array_equal(got[1], lib_ref)
+
+
+# ------------------------------------------------------------------------------------ fp32 quantile, exhaustive
+@pytest.mark.parametrize("vec4", [0, 1])
+def test_bucket_quantile_exhaustive(gswm, cuda_device, vec4):
+    """All 2^23 uniforms x both buckets: sign exact, value within 1e-6 relative of float64 ndtri."""
+    lib = gswm._lib.lib()
+    worst = 0.0
+    for bucket in (0, 1):
+        for lo in range(0, 1 << 23, 1 << 21):
+            m = np.arange(lo, lo + (1 << 21), dtype=np.uint32)
+            words = (m << np.uint32(9)) | np.uint32(0x1A5)            # low 9 bits are ignored by the kernel
+            d_w = torch.from_numpy(words.view(np.int32)).to(cuda_device)
+            d_o = torch.empty(words.size, dtype=torch.float32, device=cuda_device)
+            rc = lib.gswm_debug_bucket_quantile(d_w.data_ptr(), words.size, bucket, vec4, d_o.data_ptr(), None)
+            assert rc == 0
+            torch.cuda.synchronize()
+            got = d_o.cpu().numpy()
+            u = (m.astype(np.float64) + 0.5) * 2.0 ** -23
+            ref = O.embed_from_uniform(np.full(u.shape, bucket), u)
+            assert np.array_equal(got >= 0, ref >= 0), "bucket membership must be bit-exact"
+            assert np.array_equal(got >= 0, np.full(u.shape, bool(bucket)))
+            worst = max(worst, float(rel_err(got, ref).max()))
+    print(f"exhaustive max relative error (vec4={vec4}): {worst:.3e}")
+    assert worst <= REL_TOL
+
+
+def test_norm_ppf_f64(gswm, cuda_device):
+    lib = gswm._lib.lib()
+    rs = np.random.RandomState(1)
+    p = np.concatenate([rs.uniform(size=200000), rs.uniform(size=50000) * 1e-6, 1 - rs.uniform(size=50000) * 1e-9,
+                        2.0 ** -np.arange(1, 1070, dtype=np.float64), [0.0, 0.5, 1.0, 1 - 2.0 ** -53, 2.0 ** -54, 0.25],
+                        0.5 + (rs.uniform(size=1000) - 0.5) * 1e-12])
+    d_p = torch.from_numpy(p).to(cuda_device)
+    d_o = torch.empty_like(d_p)
+    assert lib.gswm_debug_norm_ppf(d_p.data_ptr(), p.size, d_o.data_ptr(), None) == 0
+    got = d_o.cpu().numpy()
+    ref = O.ndtri(p)
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    assert np.array_equal(np.signbit(got[ref != 0]), np.signbit(ref[ref != 0]))
+    e = rel_err(got, ref)
+    print("fp64 ppf max rel err:", e.max())
+    assert e.max() <= 1e-9
+
+
+# ------------------------------------------------------------------------------------ K2 embed
+def oracle_embed_batch(messages, keys, nonces, n, L, seed, offset, first_latent, b):
+    out = np.empty((b, n), dtype=np.float64)
+    for i in range(b):
+        k = keys[i] if isinstance(keys, list) else keys
+        no = nonces[i] if isinstance(nonces, list) else nonces
+        m = messages[i] if isinstance(messages, list) else messages
+        u = O.gswm_uniforms(seed, offset, (first_latent + i) * n, n)
+        out[i] = O.embed(m, k, no, u, L)
+    return out
+
+
+@pytest.mark.parametrize("shape,L", [((4, 64, 64), 256), ((4, 128, 128), 256), ((4, 96, 64), 96), ((4, 8, 16), 32),
+                                     ((4, 64, 64), 1024), ((4, 72, 64), 512), ((4, 160, 128), 320)])
+def test_embed_shared_key_vs_oracle(gswm, cuda_device, shape, L):
+    n = int(np.prod(shape))
+    b, seed, offset, first = 5, 0x5EED, 3, 1000
+    msg = bytes(np.random.RandomState(L).randint(0, 256, size=L // 8).astype(np.uint8))
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, L)
+    z = gswm.embed_batch(b, shape, km, seed, offset, first, cuda_device).cpu().numpy().reshape(b, n)
+    ref = oracle_embed_batch(msg, KEY, NONCE, n, L, seed, offset, first, b)
+    assert np.array_equal(z >= 0, ref >= 0), "bucket membership must be bit-exact"
+    assert rel_err(z, ref).max() <= REL_TOL
+    assert np.isfinite(z).all()
+
+
+def test_embed_per_latent_keys_vs_oracle(gswm, cuda_device):
+    rs = np.random.RandomState(77)
+    b, shape, L = 37, (4, 64, 64), 256
+    n = 16384
+    keys = [rs.bytes(32) for _ in range(b)]
+    nonces = [rs.bytes(16) for _ in range(b)]
+    msgs = [rs.bytes(32) for _ in range(b)]
+    km = gswm.KeyMaterial.make(b"".join(keys), b"".join(nonces), b"".join(msgs), L)
+    assert km.per_latent
+    z = gswm.embed_batch(b, shape, km, 99, 0, 0, cuda_device).cpu().numpy().reshape(b, n)
+    ref = oracle_embed_batch(msgs, keys, nonces, n, L, 99, 0, 0, b)
+    assert np.array_equal(z >= 0, ref >= 0)
+    assert rel_err(z, ref).max() <= REL_TOL
+
+
+def test_embed_sharding_is_transparent(gswm, cuda_device):
+    km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message("lthero", 32), 256)
+    whole = gswm.embed_batch(16, (4, 64, 64), km, 7, 0, 0, cuda_device)
+    parts = [gswm.embed_batch(4, (4, 64, 64), km, 7, 0, 4 * r, cuda_device) for r in range(4)]
+    assert torch.equal(whole, torch.cat(parts))
+
+
+def test_embed_injected_golden(gswm, cuda_device, golden, golden_arrays):
+    """Same injected uniforms as the reference run that produced the golden latent."""
+    u = np.random.RandomState(1234).uniform(size=16384)
+    km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message("lthero", 32), 256)
+    z64 = gswm.embed_batch_injected(torch.from_numpy(u).to(cuda_device), (4, 64, 64), km, 1, torch.float64).cpu().numpy()
+    z32 = gswm.embed_batch_injected(torch.from_numpy(u).to(cuda_device), (4, 64, 64), km, 1, torch.float32).cpu().numpy()
+    gold32 = golden_arrays["cli_lthero_z32"]
+    ref64 = O.embed("lthero", KEY, NONCE, u, 256).reshape(1, 4, 64, 64)
+    assert np.array_equal(z64 >= 0, ref64 >= 0)
+    assert rel_err(z64, ref64).max() <= 1e-9
+    assert rel_err(z32, gold32[None]).max() <= REL_TOL
+    c = [e for e in golden["embed_cli"] if e["name"] == "cli_lthero"][0]
+    packed = np.packbits((z32.reshape(-1) >= 0).astype(np.uint8))
+    assert sha(packed) == c["sha256_signs"]
+
+
+def test_embed_injected_edges_and_shared_u(gswm, cuda_device):
+    n = 512
+    u = np.random.RandomState(5).uniform(size=n)
+    u[:4] = [0.0, 1 - 2.0 ** -53, 2.0 ** -53, 0.5]
+    km = gswm.KeyMaterial.make(KEY, NONCE, b"abcd", 32)
+    z = gswm.embed_batch_injected(torch.from_numpy(u).to(cuda_device), (4, 8, 16), km, 3, torch.float64).cpu().numpy()
+    ref = O.embed(b"abcd", KEY, NONCE, u, 32)
+    for b in range(3):
+        got = z[b].reshape(-1)
+        assert np.array_equal(np.isinf(got), np.isinf(ref))
+        assert np.array_equal(got >= 0, ref >= 0)
+        assert rel_err(got, ref).max() <= 1e-9
+
+
+# ------------------------------------------------------------------------------------ K3 extract
+def _noisy(base, sigma, seed, dtype):
+    zn = base.astype(np.float64)
+    if sigma:
+        zn = zn + sigma * np.random.RandomState(seed).standard_normal(zn.shape)
+    return np.clip(zn, -60000.0, 8.0).astype(dtype)
+
+
+def test_extract_golden_strings(gswm, cuda_device, golden, golden_arrays):
+    base = golden_arrays["cli_lthero_z32"]
+    msg = gswm.pad_message("lthero", 32)
+    for c in golden["extract"]:
+        if "noise_seed" not in c or c["dtype"] == "float64":
+            continue
+        z = _noisy(base, c["sigma"], c["noise_seed"], c["dtype"])
+        km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
+        res = gswm.extract_batch(torch.from_numpy(z).reshape(1, 4, 64, 64).to(cuda_device), km, want_counts=True)
+        assert res.bit_strings()[0] == c["extracted_bin"], c["name"]
+        assert np.array_equal(res.counts.cpu().numpy()[0].astype(np.uint32), O.vote_counts(z, KEY, NONCE, 256))
+        assert int(res.matched[0]) == round(c["bit_accuracy"] * 256)
+        assert res.bit_accuracy() == c["bit_accuracy"]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,L", [((4, 64, 64), 256), ((4, 128, 128), 256), ((4, 64, 64), 32), ((4, 128, 128), 1024),
+                                     ((4, 96, 64), 96), ((4, 8, 16), 512), ((4, 64, 64), 2048), ((4, 160, 128), 320)])
+def test_extract_counts_vs_oracle(gswm, cuda_device, dtype, shape, L):
+    n = int(np.prod(shape))
+    b = 6
+    rs = np.random.RandomState(n + L)
+    msg = rs.bytes(L // 8)
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, L)
+    z = gswm.embed_batch(b, shape, km, 11, 0, 0, cuda_device)
+    zn = (z + 1.7 * torch.from_numpy(rs.standard_normal((b, *shape))).to(cuda_device).float()).clamp(max=8.0).to(dtype)
+    res = gswm.extract_batch(zn, km, want_counts=True)
+    zh = zn.float().cpu().numpy()
+    matched_total = 0
+    for i in range(b):
+        counts = O.vote_counts(zh[i], KEY, NONCE, L)
+        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), counts), (i, dtype)
+        bits = O.recover_message_bits(zh[i], KEY, NONCE, L)
+        assert O.bits_to_bytes(bits) == res.messages[i].cpu().numpy().tobytes()
+        m = int((bits == np.unpackbits(np.frombuffer(msg, np.uint8))).sum())
+        assert int(res.matched[i]) == m
+        matched_total += m
+    c = res.counters.cpu().numpy()
+    assert list(c) == [matched_total, b * L, int(sum(int(x) == L for x in res.matched.cpu())), b]
+
+
+def test_extract_per_latent_keys(gswm, cuda_device):
+    rs = np.random.RandomState(8)
+    b, shape, L, n = 33, (4, 64, 64), 256, 16384
+    keys = [rs.bytes(32) for _ in range(b)]
+    nonces = [rs.bytes(16) for _ in range(b)]
+    msgs = [rs.bytes(32) for _ in range(b)]
+    km = gswm.KeyMaterial.make(b"".join(keys), b"".join(nonces), b"".join(msgs), L)
+    z = gswm.embed_batch(b, shape, km, 3, 0, 0, cuda_device)
+    zn = z + 3.0 * torch.randn(z.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(1))
+    zn = zn.clamp(max=8.0)                     # the reference cannot parse cdf(z) * 2 == 2 (z >= 8.29)
+    res = gswm.extract_batch(zn, km, want_counts=True)
+    zh = zn.cpu().numpy()
+    for i in range(b):
+        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(zh[i], keys[i], nonces[i], L))
+    clean = gswm.extract_batch(z, km)
+    assert clean.messages.cpu().numpy().tobytes() == b"".join(msgs)
+    assert clean.bit_accuracy() == 1.0
+
+
+def test_extract_quantiser_edges(gswm, cuda_device, golden):
+    """-0.0 and the [-6.957e-17, 0) sliver decode as 1, exactly like int(norm.cdf(z) * 2)."""
+    vals = [float(e["z"]) for e in golden["quantise_edges"] if abs(float(e["z"])) < 1e30 or np.isinf(float(e["z"]))]
+    z = np.full(512, -1.0, dtype=np.float32)
+    z32 = np.array(vals, dtype=np.float32)
+    z[:z32.size] = z32
+    expect_bits = (z.astype(np.float64) >= O.CDF_HALF_THRESHOLD).astype(np.uint8)
+    # cross-check the closed form against scipy on the fp32 values themselves
+    assert np.array_equal(O.quantise(z.astype(np.float64)), expect_bits)
+    km = gswm.KeyMaterial.make(KEY, NONCE, None, 512)        # one copy: counts == decrypted bits
+    res = gswm.extract_batch(torch.from_numpy(z).reshape(1, 4, 8, 16).to(cuda_device), km, want_counts=True)
+    assert np.array_equal(res.counts[0].cpu().numpy().astype(np.uint32), O.vote_counts(z, KEY, NONCE, 512))
+    for dt in (torch.float16, torch.bfloat16):
+        zz = torch.tensor([0.0, -0.0, 6e-8, -6e-8, 1.0, -1.0, 8.0, -65504.0] * 64, dtype=dt)
+        res = gswm.extract_batch(zz.reshape(1, 4, 8, 16).to(cuda_device), km, want_counts=True)
+        assert np.array_equal(res.counts[0].cpu().numpy().astype(np.uint32),
+                              O.vote_counts(zz.float().numpy(), KEY, NONCE, 512))
+
+
+def test_vote_tie_decodes_zero(gswm, cuda_device):
+    # R = 2 copies that disagree everywhere -> count 1 of 2 -> strict majority fails -> all zero bits
+    L, n = 256, 512
+    ks = O.chacha20_keystream(KEY, NONCE, n // 8)
+    bits = np.unpackbits(ks)                   # decrypts to all zeros
+    bits[L:] ^= 1                              # second copy decrypts to all ones
+    z = np.where(bits == 1, 1.0, -1.0).astype(np.float32)
+    km = gswm.KeyMaterial.make(KEY, NONCE, bytes(L // 8), L)
+    res = gswm.extract_batch(torch.from_numpy(z).reshape(1, 4, 8, 16).to(cuda_device), km, want_counts=True)
+    assert (res.counts.cpu().numpy() == 1).all()
+    assert res.messages.cpu().numpy().tobytes() == bytes(L // 8)
+    assert O.recover_message(z, KEY, NONCE, L) == "0" * L
+
+
+def test_round_trip_baseline_sizes(gswm, cuda_device):
+    """BASELINE config 2/3 size (B = 4096 SD-2.1 latents): every message decodes exactly; config 4 shape."""
+    msg = gswm.pad_message("lthero", 32)
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
+    z = gswm.embed_batch(4096, (4, 64, 64), km, 0x5EED, 0, 0, cuda_device)
+    res = gswm.extract_batch(z, km)
+    assert list(res.counters.cpu().numpy()) == [4096 * 256, 4096 * 256, 4096, 4096]
+    # moments of the watermarked noise: it must still look like N(0, 1)
+    assert abs(float(z.mean())) < 2e-3 and abs(float(z.std()) - 1.0) < 2e-3
+    # sigma = 0.325 regime: ~90 % of signs agree, every message still decodes
+    noisy = z + 0.325 * torch.randn(z.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(99))
+    agree = float(((noisy >= 0) == (z >= 0)).float().mean())
+    assert 0.89 < agree < 0.91
+    res = gswm.extract_batch(noisy, km, want_counts=True)
+    assert res.bit_accuracy() == 1.0
+    sub = noisy[:16].cpu().numpy()
+    for i in range(16):
+        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(sub[i], KEY, NONCE, 256))
+    del z, noisy
+    zx = gswm.embed_batch(512, (4, 128, 128), km, 1, 0, 0, cuda_device)
+    rx = gswm.extract_batch(zx, km)
+    assert list(rx.counters.cpu().numpy()) == [512 * 256, 512 * 256, 512, 512]
+
+
+# ------------------------------------------------------------------------------------ host-buffer pipe
+def test_host_pipe_matches_device_api(gswm, cuda_device):
+    msg = gswm.pad_message("lthero", 32)
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
+    pipe = gswm.HostPipe(0, max_elems=16384, chunk_latents=8)
+    out = torch.empty((27, 4, 64, 64), dtype=torch.float32).pin_memory()
+    pipe.embed(out, km, 5, 0, 100)
+    dev = gswm.embed_batch(27, (4, 64, 64), km, 5, 0, 100, cuda_device)
+    assert torch.equal(out, dev.cpu())
+    noisy = (out + 2.0 * torch.randn(out.shape, generator=torch.Generator().manual_seed(3)))
+    msgs, cnt, matched, counters = pipe.extract(noisy, km, want_counts=True)
+    r = gswm.extract_batch(noisy.to(cuda_device), km, want_counts=True)
+    assert np.array_equal(msgs, r.messages.cpu().numpy())
+    assert np.array_equal(cnt, r.counts.cpu().numpy())
+    assert np.array_equal(matched, r.matched.cpu().numpy())
+    assert np.array_equal(counters, r.counters.cpu().numpy())
+    # fp16 host input, per-latent keys
+    rs = np.random.RandomState(4)
+    kmp = gswm.KeyMaterial.make(rs.bytes(32 * 27), rs.bytes(16 * 27), rs.bytes(32 * 27), 256)
+    pipe.embed(out, kmp, 6)
+    m2, _, mt2, c2 = pipe.extract(out.half(), kmp)
+    assert m2.tobytes() == kmp.msgs.tobytes() and list(c2) == [27 * 256, 27 * 256, 27, 27]
+    u = np.random.RandomState(1234).uniform(size=16384)
+    zi = pipe.embed_injected(u, (4, 64, 64), km, 1, np.float64)
+    assert rel_err(zi.reshape(-1), O.embed("lthero", KEY, NONCE, u, 256)).max() <= 1e-9
+    pipe.close()
+
+
+# ------------------------------------------------------------------------------------ reference-named drop-ins
+def test_dropin_gs_insert_and_extract(gswm, cuda_device, golden, golden_arrays, tmp_path, monkeypatch):
+    from gswm import extract as gx
+    from gswm import gs_insert as gi
+
+    monkeypatch.chdir(tmp_path)
+    opt = types.SimpleNamespace(key_hex=O.DEFAULT_KEY_HEX, nonce_hex=O.DEFAULT_NONCE_HEX)
+    np.random.seed(1234)                      # same stream as RandomState(1234) used for the golden run
+    z = gi.gs_watermark_init_noise(opt, "lthero")
+    assert z.shape == (4, 64, 64) and z.dtype == np.float64
+    assert rel_err(z.reshape(-1)[:512], golden_arrays["cli_lthero_z64_head"]).max() <= 1e-9
+    assert np.array_equal(z.astype(np.float32) >= 0, golden_arrays["cli_lthero_z32"] >= 0)
+    lines = (tmp_path / "info_data.txt").read_text().splitlines()
+    assert lines[1:] == golden["info_data_cli_tail"][1:] and lines[0].startswith("Time: ")
+    opt.nonce_hex = ""                        # nonce falls back to key_hex[16:48]
+    np.random.seed(1236)
+    z2 = gi.gs_watermark_init_noise(opt, "lthero")
+    c = [e for e in golden["embed_cli"] if e["name"] == "cli_nonce_fallback"][0]
+    assert sha(np.packbits((z2.reshape(-1) >= 0).astype(np.uint8))) == c["sha256_signs"]
+
+    args = types.SimpleNamespace(key=KEY, nonce=NONCE, l=1, message_length=256)
+    base = golden_arrays["cli_lthero_z32"]
+    for c in golden["extract"]:
+        if "noise_seed" not in c:
+            continue
+        zt = torch.from_numpy(_noisy(base, c["sigma"], c["noise_seed"], c["dtype"])).reshape(1, 4, 64, 64)
+        got = gx.recover_exactracted_message(zt, args)
+        assert got == c["extracted_bin"], c["name"]
+        orig, acc = gx.calculate_bit_accuracy((b"lthero" + bytes(26)).hex(), got)
+        assert acc == c["bit_accuracy"] and orig == c["original_bin"]
+    for bad in golden["quantise_raises"]:
+        t = torch.full((1, 1, 16, 32), 0.5, dtype=torch.float64)
+        t[0, 0, 0, 0] = float(bad["z"])
+        with pytest.raises(ValueError):
+            gx.recover_exactracted_message(t, types.SimpleNamespace(key=KEY, nonce=NONCE, l=1, message_length=512))
+    batch = gi.gs_watermark_init_noise_batch(opt, "lthero", n_samples=5, seed=1)
+    assert batch.shape == (5, 4, 64, 64) and batch.is_cuda
+
+
+def test_argument_errors(gswm, cuda_device):
+    km = gswm.KeyMaterial.make(KEY, NONCE, bytes(32), 256)
+    with pytest.raises(ValueError):
+        gswm.embed_batch(1, (4, 5, 5), km, 0, device=cuda_device)          # not a multiple of 512
+    with pytest.raises(ValueError):
+        gswm.extract_batch(torch.zeros((1, 4, 96, 64), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 1024))
+    lib = gswm._lib.lib()
+    job = gswm._lib.Job(1, 16384, 256, 0, 1, 1, 1)
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -7              # misaligned key pointer
+    job = gswm._lib.Job(1, 16384, 250, 0, 16, 16, 16)
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -3
+    job = gswm._lib.Job(1, 1000, 32, 0, 16, 16, 16)
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -2
+    assert lib.gswm_embed(None, 0, 0, 0, 16, 16, None) == -1
+    assert "multiple of 512" in gswm._lib.strerror(-2)

@@ -1,0 +1,186 @@
+"""CPU-only checks of the host side: the C-ABI library builds/loads and exports everything
+include/gswm.h declares (no compute calls without a GPU), framing / key-resolution logic against the
+oracle, argument validation, and the world_size-2 sharding + counter all-reduce logic over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import gs_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gswm():
+    import gswm as g
+    g.build()            # nvcc cross-compiles for sm_100a without a GPU
+    return g
+
+
+def test_library_exports_every_declared_symbol(gswm):
+    header = open(os.path.join(ROOT, "include", "gswm.h")).read()
+    declared = set(re.findall(r"\b(gswm_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gswm_workspace_bytes()", }
+    assert {"gswm_embed", "gswm_extract", "gswm_chacha20_keystream", "gswm_pipe_extract"} <= declared
+    lib = gswm._lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libgswm.so does not export {name}"
+    assert set(gswm._lib.EXPORTS) == declared
+    out = subprocess.run(["nm", "-D", "--defined-only", gswm._lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", out), name
+
+
+def test_library_is_sm100a(gswm):
+    out = subprocess.run(["cuobjdump", "-lelf", gswm._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_abi_basics_without_gpu(gswm):
+    lib = gswm._lib.lib()
+    assert lib.gswm_abi_version() == 1
+    assert gswm._lib.strerror(0) == "success"
+    for code in range(-7, 0):
+        assert gswm._lib.strerror(code).startswith("gswm:")
+    job = gswm._lib.Job(3, 16384, 256, 0, None, None, None)
+    assert lib.gswm_workspace_bytes(C.byref(job)) == 2048
+    job.per_latent = 1
+    assert lib.gswm_workspace_bytes(C.byref(job)) == 0
+    # argument validation happens before any CUDA call
+    assert lib.gswm_embed(None, 0, 0, 0, None, None, None) == -1
+    bad = gswm._lib.Job(1, 1000, 32, 0, 16, 16, 16)
+    assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, 16, None) == -2
+    bad = gswm._lib.Job(1, 16384, 48, 0, 16, 16, 16)
+    assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, 16, None) == -3
+    bad = gswm._lib.Job(1, 16384, 640, 0, 16, 16, 16)           # 640 does not divide 16384
+    assert lib.gswm_extract(C.byref(bad), 16, 0, 16, None, None, None, 16, None) == -3
+    ok = gswm._lib.Job(1, 16384, 256, 0, 16, 16, 16)
+    assert lib.gswm_extract(C.byref(ok), 16, 7, 16, None, None, None, 16, None) == -4
+    assert lib.gswm_extract(C.byref(ok), 8, 0, 16, None, None, None, 16, None) == -7
+    assert lib.gswm_chacha20_keystream(16, 16, 1, 100, 16, None) == -2
+
+
+def test_no_cpu_path(gswm):
+    import torch
+    km = gswm.KeyMaterial.make(bytes(32), bytes(16), bytes(32), 256)
+    with pytest.raises(ValueError):
+        gswm.embed_batch(1, (4, 64, 64), km, 0, device="cpu")
+    with pytest.raises(ValueError):
+        gswm.extract_batch(torch.zeros(1, 4, 64, 64), km)
+
+
+def test_pad_message_matches_oracle(gswm):
+    for msg, nb in [("lthero", 32), ("x" * 40, 32), ("水印-λ-✓", 32), ("ab", 4), (b"\x01\x02", 8), ("lthero", 128)]:
+        assert gswm.pad_message(msg, nb) == O.pad_message(msg, nb)
+    assert gswm.pad_message("lthero12", 32, use_repeat=True) == O.frame_message("lthero12", 16384, 256, use_repeat=True)[0]
+    assert gswm.pad_message("ab", 32, use_repeat=True) == (b"ab" + bytes(6)) * 4
+    r1, r2 = gswm.pad_message("", 32), gswm.pad_message("", 32)
+    assert len(r1) == 32 and r1 != r2            # empty message -> os.urandom (gs_insert.py:18-20)
+
+
+def test_resolve_key_nonce(gswm):
+    k, n = gswm.resolve_key_nonce(O.DEFAULT_KEY_HEX, O.DEFAULT_NONCE_HEX)
+    assert (k, n) == O.resolve_key_nonce(O.DEFAULT_KEY_HEX, O.DEFAULT_NONCE_HEX)
+    k, n = gswm.resolve_key_nonce(O.DEFAULT_KEY_HEX, "")
+    assert n.hex() == O.DEFAULT_KEY_HEX[16:48] and (k, n) == O.resolve_key_nonce(O.DEFAULT_KEY_HEX, "")
+    k, n = gswm.resolve_key_nonce("", "")
+    assert len(k) == 32 and len(n) == 16
+    with pytest.raises(ValueError):
+        gswm.resolve_key_nonce("zz" * 32, "")
+    with pytest.raises(ValueError):
+        gswm.resolve_key_nonce("00" * 16, "00" * 16)
+    with pytest.raises(ValueError):
+        gswm.resolve_key_nonce("00" * 32, "00" * 8)
+
+
+def test_choose_watermark_length(gswm):
+    for n in [256, 2047, 2048, 4096, 8192, 16384, 32768, 65536, 1 << 22]:
+        assert gswm.choose_watermark_length(n) == O.choose_watermark_length(n)
+
+
+def test_key_material_shapes(gswm):
+    km = gswm.KeyMaterial.make(bytes(32), bytes(16), bytes(32), 256)
+    assert not km.per_latent and km.rows == 1
+    km = gswm.KeyMaterial.make(bytes(32 * 5), bytes(16 * 5), bytes(32 * 5), 256)
+    assert km.per_latent and km.rows == 5
+    km = gswm.KeyMaterial.make(bytes(32), bytes(16), bytes(32 * 5), 256)      # shared key, per-latent message
+    assert km.rows == 5 and km.keys.shape == (5, 32)
+    with pytest.raises(ValueError):
+        gswm.KeyMaterial.make(bytes(31), bytes(16), bytes(32), 256)
+    with pytest.raises(ValueError):
+        gswm.KeyMaterial.make(bytes(32 * 2), bytes(16 * 3), bytes(32), 256)
+    with pytest.raises(ValueError):
+        gswm.KeyMaterial.make(bytes(32), bytes(16), bytes(32), 100)
+
+
+def test_calculate_bit_accuracy_matches_reference_vectors(gswm, golden):
+    from gswm.extract import calculate_bit_accuracy
+    for c in golden["bit_accuracy"]:
+        o, a = calculate_bit_accuracy(c["original_message_hex"], c["extracted"])
+        assert o == c["original_bin"] and a == c["accuracy"]
+
+
+def test_two_rank_sharding_and_counter_allreduce_gloo(tmp_path):
+    """world_size 2 over gloo on CPU: contiguous batch shards keyed by global latent index reproduce the single-rank
+    uniforms, and the all-reduced counters equal the whole-batch counters (the oracle stands in for the kernels)."""
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, 'a-watermark-for-diffusion-models_b200'))
+from oracle import gs_oracle as O
+from gswm.sharding import shard_range
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+B, n, L, seed = 6, 512, 32, 9
+key, nonce = bytes.fromhex(O.DEFAULT_KEY_HEX), bytes.fromhex(O.DEFAULT_NONCE_HEX)
+lo, hi = shard_range(B, rank, world)
+counters = torch.zeros(4, dtype=torch.int64)
+zs = []
+for g in range(lo, hi):
+    z = O.embed(b'abcd', key, nonce, O.gswm_uniforms(seed, 0, g * n, n), L)
+    zs.append(z)
+    zn = z + 2.5 * np.random.RandomState(g).standard_normal(n)
+    bits = O.recover_message_bits(np.clip(zn, None, 8.0), key, nonce, L)
+    m = int((bits == np.unpackbits(np.frombuffer(b'abcd', np.uint8))).sum())
+    counters += torch.tensor([m, L, int(m == L), 1])
+dist.all_reduce(counters)
+gathered = [None] * world
+dist.all_gather_object(gathered, np.stack(zs))
+if rank == 0:
+    np.save({str(tmp_path)!r} + '/z.npy', np.concatenate(gathered))
+    np.save({str(tmp_path)!r} + '/c.npy', counters.numpy())
+dist.destroy_process_group()
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29531", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    z = np.load(tmp_path / "z.npy")
+    c = np.load(tmp_path / "c.npy")
+    key, nonce = bytes.fromhex(O.DEFAULT_KEY_HEX), bytes.fromhex(O.DEFAULT_NONCE_HEX)
+    B, n, L = 6, 512, 32
+    whole = np.stack([O.embed(b"abcd", key, nonce, O.gswm_uniforms(9, 0, g * n, n), L) for g in range(B)])
+    assert np.array_equal(z, whole)
+    tot = np.zeros(4, dtype=np.int64)
+    for g in range(B):
+        zn = whole[g] + 2.5 * np.random.RandomState(g).standard_normal(n)
+        bits = O.recover_message_bits(np.clip(zn, None, 8.0), key, nonce, L)
+        m = int((bits == np.unpackbits(np.frombuffer(b"abcd", np.uint8))).sum())
+        tot += [m, L, int(m == L), 1]
+    assert np.array_equal(c, tot)
+
+
+def test_shard_range(gswm):
+    from gswm.sharding import shard_range
+    for b in [0, 1, 7, 8, 4096, 65537]:
+        for w in [1, 2, 3, 8]:
+            rs = [shard_range(b, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == b
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in rs]
+            assert max(sizes) - min(sizes) <= 1
