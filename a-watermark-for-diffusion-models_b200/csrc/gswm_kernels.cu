@@ -14,7 +14,9 @@
 #include <math_constants.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <random>
 
 #include "../../include/gswm.h"
 #include "gswm_math.cuh"
@@ -79,93 +81,177 @@ chacha20_keystream_kernel(const uint8_t* __restrict__ keys, const uint8_t* __res
   }
 }
 
-// Fill a tile's keystream words in shared memory.
-//  kPerLatent: warp 0 computes them (lane = ChaCha block);  else: copy the slice of the precomputed
-//  table (workspace).  `words` = number of valid words in this tile (multiple of 16).
-template <bool kPerLatent>
-__device__ __forceinline__ void stage_tile_keystream(uint32_t* __restrict__ s_ks, const uint8_t* __restrict__ keys,
-                                                     const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
-                                                     const uint32_t* __restrict__ table, int64_t latent, uint32_t tile,
-                                                     uint32_t words, uint32_t msg_words, uint32_t tiled_words) {
-  if constexpr (kPerLatent) {
-    if (threadIdx.x < 32 && threadIdx.x * 16 < words) {
-      uint32_t k[8], n[4], ks[16];
-      load_key_nonce(keys, nonces, latent, k, n);
-      const uint32_t blk = tile * 32 + threadIdx.x;
-      chacha20_block(k, n, blk, ks);
-      // lane-strided 16-byte stores: lane l owns words [16 l, 16 l + 16)
-      uint4* dst = reinterpret_cast<uint4*>(s_ks + threadIdx.x * 16);
+// ------------------------------------------------------------------------------------------------
+// Tile keystream staging.
+//
+// per-latent keys : warp 0 of the CTA computes its tile's 32 ChaCha blocks (lane = block) straight
+//                   into shared memory.
+// shared key      : every latent needs the same keystream, so it is computed ONCE per launch, inside
+//                   the same kernel (no second launch, no dependent-launch gap): the CTAs that are
+//                   dispatched first each produce one tile-sized slice into the workspace table and
+//                   publish it with a release store of this launch's unique epoch; every CTA then
+//                   acquires the slice it needs (spin on the flag, L2 loads) into shared memory.
+//                   Producers are the lowest-numbered CTAs of the grid, which the hardware dispatches
+//                   no later than any consumer, so the wait cannot deadlock.
+// ------------------------------------------------------------------------------------------------
+struct SharedTable {
+  uint32_t* table;              // [tiles_per_latent][kTileWords]
+  unsigned long long* flags;    // [tiles_per_latent], == epoch once the slice is complete
+  unsigned long long epoch;     // unique per launch
+};
+
+// lane `lane` of one warp: ChaCha block `tile*32 + lane` of stream `row`, XOR tiled message, 64 bytes to dst
+__device__ __forceinline__ void chacha_tile_lane(uint32_t* __restrict__ dst, const uint8_t* __restrict__ keys,
+                                                 const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
+                                                 int64_t row, uint32_t tile, uint32_t lane, uint32_t msg_words,
+                                                 uint32_t tiled_words) {
+  uint32_t k[8], n[4], ks[16];
+  load_key_nonce(keys, nonces, row, k, n);
+  const uint32_t blk = tile * 32 + lane;
+  chacha20_block(k, n, blk, ks);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + lane * 16);     // lane l owns words [16 l, 16 l + 16)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 v;
-        v.x = ks[4 * q + 0] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 0, msg_words, tiled_words);
-        v.y = ks[4 * q + 1] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 1, msg_words, tiled_words);
-        v.z = ks[4 * q + 2] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 2, msg_words, tiled_words);
-        v.w = ks[4 * q + 3] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 3, msg_words, tiled_words);
-        dst[q] = v;
-      }
-    }
-  } else {
-    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)tile * kTileWords);
-    if (threadIdx.x * 4 < words) reinterpret_cast<uint4*>(s_ks)[threadIdx.x] = __ldg(src + threadIdx.x);
+  for (int q = 0; q < 4; ++q) {
+    uint4 v;
+    v.x = ks[4 * q + 0] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 0, msg_words, tiled_words);
+    v.y = ks[4 * q + 1] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 1, msg_words, tiled_words);
+    v.z = ks[4 * q + 2] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 2, msg_words, tiled_words);
+    v.w = ks[4 * q + 3] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 3, msg_words, tiled_words);
+    d4[q] = v;
   }
+}
+
+__device__ __forceinline__ uint32_t tile_words(int64_t n_elems, uint32_t tile) {
+  const int64_t remain = n_elems - (int64_t)tile * kTileElems;
+  return (uint32_t)(remain < kTileElems ? remain : kTileElems) >> 5;     // multiple of 16
+}
+
+// Producer side (shared key): warp 0 writes slice `tile` of the table and publishes it.
+__device__ __forceinline__ void publish_shared_slice(const SharedTable& tab, const uint8_t* __restrict__ keys,
+                                                     const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
+                                                     int64_t n_elems, uint32_t tile, uint32_t msg_words, uint32_t tiled_words) {
+  if (threadIdx.x < 32) {
+    if (threadIdx.x * 16 < tile_words(n_elems, tile))
+      chacha_tile_lane(tab.table + (size_t)tile * kTileWords, keys, nonces, msg, 0, tile, threadIdx.x, msg_words, tiled_words);
+    __threadfence();                                   // each lane's slice stores before the flag
+    __syncwarp();
+    if (threadIdx.x == 0) {
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(tab.flags + tile), "l"(tab.epoch) : "memory");
+    }
+  }
+}
+
+// Consumer side (shared key): wait for slice `tile`, copy it to shared memory (L2 loads: the producer ran on
+// another SM, L1 is not coherent).  Ends with the data visible to the whole CTA.
+__device__ __forceinline__ void acquire_shared_slice(uint32_t* __restrict__ s_ks, const SharedTable& tab, uint32_t tile,
+                                                     uint32_t words) {
+  if (threadIdx.x == 0) {
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(tab.flags + tile) : "memory");
+      if (seen != tab.epoch) __nanosleep(100);
+    } while (seen != tab.epoch);
+  }
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(tab.table + (size_t)tile * kTileWords);
+  if (threadIdx.x * 4 < words) reinterpret_cast<uint4*>(s_ks)[threadIdx.x] = __ldcg(src + threadIdx.x);
+  __syncthreads();
+}
+
+// Per-latent keys: warp 0 computes the tile in place.
+__device__ __forceinline__ void compute_private_slice(uint32_t* __restrict__ s_ks, const uint8_t* __restrict__ keys,
+                                                      const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
+                                                      int64_t latent, uint32_t tile, uint32_t words, uint32_t msg_words,
+                                                      uint32_t tiled_words) {
+  if (threadIdx.x < 32 && threadIdx.x * 16 < words)
+    chacha_tile_lane(s_ks, keys, nonces, msg, latent, tile, threadIdx.x, msg_words, tiled_words);
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: embed.  grid = n_latents * tiles_per_latent CTAs, one tile each.
 //   bits  <- keystream XOR tiled message                                (gs_insert.py:23,45-49)
-//   u     <- Philox4x32-10 word, 23 bits                               (stands in for gs_insert.py:62)
-//   z     <- Phi^-1((u + y)/2) via bucket_quantile_f32                  (gs_insert.py:64)
+//   u     <- 23 bits of Philox4x32 per element (3 calls feed 16 elements) (stands in for gs_insert.py:62)
+//   z     <- Phi^-1((u + y)/2) = +-g(v) via bucket_quantile4_f32          (gs_insert.py:64)
 //   store <- one 128-bit store per 4 elements, C-order flat index       (gs_insert.py:65)
 // ------------------------------------------------------------------------------------------------
 struct EmbedArgs {
   const uint8_t* keys;
   const uint8_t* nonces;
   const uint8_t* msgs;
-  const uint32_t* table;     // shared-key bucket-bit table (keystream ^ tiled message)
+  SharedTable tab;           // shared-key bucket-bit table (keystream ^ tiled message)
   float* out;
   int64_t n_elems;
   int64_t first_latent;      // global index of latent 0 (sharding)
-  uint32_t tiles_per_latent;
   uint32_t msg_words;
   uint32_t tiled_words;
   uint32_t msg_stride_bytes;
-  uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  uint32_t seed_lo, seed_hi, off_lo, off_hi;   // off_hi holds (offset_hi << 2): its low 2 bits select the Philox call
 };
 
+// grid = (n_latents, tiles_per_latent): blockIdx.x = latent, blockIdx.y = tile.
 template <bool kPerLatent>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void embed_stage(uint32_t* s_ks, const EmbedArgs& a, int64_t latent, uint32_t tile, uint32_t words) {
+  if constexpr (kPerLatent) {
+    compute_private_slice(s_ks, a.keys, a.nonces, a.msgs + latent * (int64_t)a.msg_stride_bytes, latent, tile, words,
+                          a.msg_words, a.tiled_words);
+  } else {
+    if (blockIdx.x == 0) publish_shared_slice(a.tab, a.keys, a.nonces, a.msgs, a.n_elems, tile, a.msg_words, a.tiled_words);
+    acquire_shared_slice(s_ks, a.tab, tile, words);
+  }
+}
+
+// Sign look-up: for a byte of bucket bits, +-1.0f for the four elements of its high nibble (even float4)
+// and of its low nibble (odd float4); +1 where the bucket bit is 1.  256 entries x 2 x float4 = 8 KB.
+__device__ __forceinline__ void build_sign_lut(float4* lut) {
+  const uint32_t b = threadIdx.x;                  // kThreads == 256: one byte value per thread
+  lut[2 * b + 0] = make_float4((b & 0x80u) ? 1.f : -1.f, (b & 0x40u) ? 1.f : -1.f, (b & 0x20u) ? 1.f : -1.f, (b & 0x10u) ? 1.f : -1.f);
+  lut[2 * b + 1] = make_float4((b & 0x08u) ? 1.f : -1.f, (b & 0x04u) ? 1.f : -1.f, (b & 0x02u) ? 1.f : -1.f, (b & 0x01u) ? 1.f : -1.f);
+}
+
+template <bool kPerLatent>
+__global__ void __launch_bounds__(kThreads, 6)
 embed_kernel(const EmbedArgs a) {
   __shared__ __align__(16) uint32_t s_ks[kTileWords];
-  const int64_t latent = blockIdx.x / a.tiles_per_latent;
-  const uint32_t tile = blockIdx.x - (uint32_t)latent * a.tiles_per_latent;
+  __shared__ __align__(16) float4 s_sign[512];
+  const int64_t latent = blockIdx.x;
+  const uint32_t tile = blockIdx.y;
   const int64_t tile_base = (int64_t)tile * kTileElems;
-  const int64_t remain = a.n_elems - tile_base;
-  const uint32_t n_f4 = (uint32_t)(remain < kTileElems ? remain : kTileElems) >> 2;   // multiple of 128
-
-  const uint8_t* msg = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
-  stage_tile_keystream<kPerLatent>(s_ks, a.keys, a.nonces, msg, a.table, latent, tile, n_f4 >> 3,
-                                   a.msg_words, a.tiled_words);
-  __syncthreads();
+  const uint32_t words = tile_words(a.n_elems, tile);
+  const uint32_t n_f4 = words << 3;                                   // multiple of 128
+  build_sign_lut(s_sign);
+  embed_stage<kPerLatent>(s_ks, a, latent, tile, words);             // ends with __syncthreads()
 
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
-  // global group index of this tile's first float4 (Philox counter), 64-bit
-  const uint64_t g0 = (uint64_t)((a.first_latent + latent) * a.n_elems + tile_base) >> 2;
   float4* out4 = reinterpret_cast<float4*>(a.out + latent * a.n_elems + tile_base);
+  // Philox counter of this thread's super-iteration s: G = ((global_latent * tiles + tile) * 4 + s) * 256 + tid
+  const uint64_t g_tile = ((uint64_t)(a.first_latent + latent) * gridDim.y + tile) * (4ull * kThreads) + threadIdx.x;
+  const float4* my_sign = s_sign + (threadIdx.x & 1u);               // i & 1 == threadIdx.x & 1 for every float4
 
-  const uint32_t nib_shift = (threadIdx.x & 1u) ? 0u : 4u;
+  auto emit = [&](uint32_t i, uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, bool guard) {
+    if (guard && i >= n_f4) return;
+    // bucket bits of elements 4i..4i+3: byte i>>1 of the tile's (keystream ^ message), high nibble first
+    const float4 sgn = my_sign[2u * s_bytes[i >> 1]];
+    out4[i] = bucket_quantile4_f32(f0, f1, f2, f3, sgn);
+  };
+  auto super_iteration = [&](uint32_t sidx, bool guard) {
+    const uint64_t g = g_tile + (uint64_t)sidx * kThreads;
+    const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
+    const uint4 c0 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 0u), a.seed_lo, a.seed_hi);
+    const uint4 c1 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 1u), a.seed_lo, a.seed_hi);
+    const uint4 c2 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 2u), a.seed_lo, a.seed_hi);
+    const uint32_t i0 = (4u * sidx) * kThreads + threadIdx.x;
+    emit(i0, fbits_top23(c0.x), fbits_top23(c0.y), fbits_top23(c0.z), fbits_top23(c0.w), guard);
+    emit(i0 + kThreads, fbits_top23(c1.x), fbits_top23(c1.y), fbits_top23(c1.z), fbits_top23(c1.w), guard);
+    emit(i0 + 2 * kThreads, fbits_top23(c2.x), fbits_top23(c2.y), fbits_top23(c2.z), fbits_top23(c2.w), guard);
+    emit(i0 + 3 * kThreads, fbits_low_bytes(c0.x, c1.x, c2.x), fbits_low_bytes(c0.y, c1.y, c2.y),
+         fbits_low_bytes(c0.z, c1.z, c2.z), fbits_low_bytes(c0.w, c1.w, c2.w), guard);
+  };
+  if (n_f4 == kTileF4) {                       // full tile: constant trip count, no bounds checks
 #pragma unroll 2
-  for (uint32_t i = threadIdx.x; i < n_f4; i += kThreads) {
-    const uint64_t g = g0 + i;
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), a.off_lo, a.off_hi),
-                                  a.seed_lo, a.seed_hi);
-    // 4 bucket bits of elements 4i..4i+3: byte i>>1, high nibble first (MSB-first bit order);
-    // i & 1 == threadIdx.x & 1 for every iteration, so the nibble shift is loop-invariant.
-    const uint32_t nib = (uint32_t)s_bytes[i >> 1] >> nib_shift;     // bits 3..0 = elements 0..3
-    uint32_t f0, f1, f2, f3;
-    nibble_flip_masks(nib, f0, f1, f2, f3);
-    const float4 z = bucket_quantile4_f32(r, f0, f1, f2, f3);
-    out4[i] = z;
+    for (uint32_t sidx = 0; sidx < 4; ++sidx) super_iteration(sidx, false);
+  } else {
+    for (uint32_t sidx = 0; sidx * 4 * kThreads < n_f4; ++sidx) super_iteration(sidx, true);
   }
 }
 
@@ -174,15 +260,12 @@ template <bool kPerLatent, typename OutT>
 __global__ void __launch_bounds__(kThreads)
 embed_injected_kernel(const EmbedArgs a, const double* __restrict__ u, int u_per_latent, OutT* __restrict__ out) {
   __shared__ __align__(16) uint32_t s_ks[kTileWords];
-  const int64_t latent = blockIdx.x / a.tiles_per_latent;
-  const uint32_t tile = blockIdx.x - (uint32_t)latent * a.tiles_per_latent;
+  const int64_t latent = blockIdx.x;
+  const uint32_t tile = blockIdx.y;
   const int64_t tile_base = (int64_t)tile * kTileElems;
-  const int64_t remain = a.n_elems - tile_base;
-  const uint32_t n_el = (uint32_t)(remain < kTileElems ? remain : kTileElems);
-  const uint8_t* msg = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
-  stage_tile_keystream<kPerLatent>(s_ks, a.keys, a.nonces, msg, a.table, latent, tile, n_el >> 5,
-                                   a.msg_words, a.tiled_words);
-  __syncthreads();
+  const uint32_t words = tile_words(a.n_elems, tile);
+  const uint32_t n_el = words << 5;
+  embed_stage<kPerLatent>(s_ks, a, latent, tile, words);
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
   const double* up = u + (u_per_latent ? latent * a.n_elems : 0) + tile_base;
   OutT* op = out + latent * a.n_elems + tile_base;
@@ -207,7 +290,7 @@ struct ExtractArgs {
   const uint8_t* keys;
   const uint8_t* nonces;
   const uint8_t* msgs;        // reference messages (may be null)
-  const uint32_t* table;      // shared-key keystream table
+  SharedTable tab;            // shared-key keystream table
   const void* z;
   uint8_t* msg_out;
   uint16_t* counts;
@@ -268,6 +351,10 @@ extract_kernel(const ExtractArgs a) {
 
   for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) s_cnt[p] = 0;
   if (threadIdx.x == 0) s_matched = 0;
+  if constexpr (!kPerLatent) {                  // the first CTAs each produce slices of the shared keystream
+    for (uint32_t t = blockIdx.x; t < a.tiles_per_latent; t += gridDim.x)
+      publish_shared_slice(a.tab, a.keys, a.nonces, nullptr, a.n_elems, t, 0, 0);
+  }
 
   uint32_t packed = 0;                          // kPow2: byte lane k = count of element (3-k)
   uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;      // spilled byte lanes (only for very large latents)
@@ -275,11 +362,11 @@ extract_kernel(const ExtractArgs a) {
 
   for (uint32_t tile = 0; tile < a.tiles_per_latent; ++tile) {
     const int64_t tile_base = (int64_t)tile * kTileElems;
-    const int64_t remain = a.n_elems - tile_base;
-    const uint32_t n_f4 = (uint32_t)(remain < kTileElems ? remain : kTileElems) >> 2;
+    const uint32_t words = tile_words(a.n_elems, tile);
+    const uint32_t n_f4 = words << 3;
     __syncthreads();                            // previous tile's keystream no longer needed
-    stage_tile_keystream<kPerLatent>(s_ks, a.keys, a.nonces, nullptr, a.table, latent, tile, n_f4 >> 3, 0, 0);
-    __syncthreads();
+    if constexpr (kPerLatent) compute_private_slice(s_ks, a.keys, a.nonces, nullptr, latent, tile, words, 0, 0);
+    else acquire_shared_slice(s_ks, a.tab, tile, words);
     const size_t zt = z_g0 + (size_t)(tile_base >> 2);
 #pragma unroll 4
     for (uint32_t i = threadIdx.x; i < n_f4; i += kThreads) {
@@ -349,18 +436,19 @@ extract_kernel(const ExtractArgs a) {
 }
 
 // Test hook: evaluate the fp32 bucket quantile on caller-supplied raw words (exhaustive accuracy test).
+// m = w >> 9; bucket bit 1: z = +g((m + 1/2) 2^-23); bucket bit 0: z = -g(.) (so the reference's u is 1 - v).
 __global__ void __launch_bounds__(kThreads)
 debug_quantile_kernel(const uint32_t* __restrict__ w, int64_t n, uint32_t bucket_bit, int use_vec4, float* __restrict__ out) {
   const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
   if (i >= n) return;
-  const uint32_t flip = bucket_bit ? 0u : 0xFFFFFFFFu;
+  const float s = bucket_bit ? 1.f : -1.f;
   const uint4 r = *reinterpret_cast<const uint4*>(w + i);
   float4 z;
   if (use_vec4) {
-    z = bucket_quantile4_f32(r, flip, flip, flip, flip);
+    z = bucket_quantile4_f32(fbits_top23(r.x), fbits_top23(r.y), fbits_top23(r.z), fbits_top23(r.w), make_float4(s, s, s, s));
   } else {
-    z = make_float4(bucket_quantile_f32(r.x, flip), bucket_quantile_f32(r.y, flip), bucket_quantile_f32(r.z, flip),
-                    bucket_quantile_f32(r.w, flip));
+    z = make_float4(s * halfnormal_quantile(fbits_top23(r.x)), s * halfnormal_quantile(fbits_top23(r.y)),
+                    s * halfnormal_quantile(fbits_top23(r.z)), s * halfnormal_quantile(fbits_top23(r.w)));
   }
   *reinterpret_cast<float4*>(out + i) = z;
 }
@@ -384,33 +472,49 @@ static int check_job(const gswm_job* job, bool for_extract) {
   if (for_extract && (job->n_elems % job->msg_bits) != 0) return GSWM_E_MSGLEN;
   if (job->n_elems > ((int64_t)1 << 31)) return GSWM_E_RANGE;
   const int64_t tiles = (job->n_elems + kTileElems - 1) / kTileElems;
-  if (job->n_latents * tiles > 0x7FFFFFFFll) return GSWM_E_RANGE;
+  if (job->n_latents > 0x7FFFFFFFll || tiles > 65535) return GSWM_E_RANGE;
   return GSWM_OK;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int launch_table(const gswm_job* job, bool with_msg, void* d_workspace, cudaStream_t st) {
-  if (!d_workspace) return GSWM_E_WORKSPACE;
-  if (!aligned16(d_workspace)) return GSWM_E_ALIGN;
-  const uint32_t blocks = (uint32_t)(job->n_elems / 512);
-  const uint32_t msg_words = (uint32_t)job->msg_bits / 32;
-  const uint32_t tiled_words = (uint32_t)(job->n_elems / job->msg_bits) * msg_words;
-  chacha20_keystream_kernel<<<(blocks + kThreads - 1) / kThreads, kThreads, 0, st>>>(
-      job->d_keys, job->d_nonces, with_msg ? job->d_msgs : nullptr, 1, blocks, msg_words, tiled_words, 0,
-      reinterpret_cast<uint32_t*>(d_workspace));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
+static uint32_t tiles_of(int64_t n_elems) { return (uint32_t)((n_elems + kTileElems - 1) / kTileElems); }
+
+static size_t shared_workspace_bytes(int64_t n_elems) {
+  const size_t tiles = tiles_of(n_elems);
+  return tiles * (size_t)kTileWords * 4 + ((tiles * 8 + 15) & ~(size_t)15);
 }
 
-static EmbedArgs make_embed_args(const gswm_job* job, void* d_workspace) {
+// A value no earlier launch (and, with overwhelming probability, no stale memory) carries.
+static unsigned long long next_epoch() {
+  static std::atomic<unsigned long long> epoch{[] {
+    std::random_device rd;
+    return ((unsigned long long)rd() << 32) ^ (unsigned long long)rd() ^
+           (unsigned long long)std::chrono::steady_clock::now().time_since_epoch().count();
+  }()};
+  unsigned long long e;
+  do { e = epoch.fetch_add(1, std::memory_order_relaxed) + 1; } while (e == 0);
+  return e;
+}
+
+static int make_shared_table(const gswm_job* job, void* d_workspace, SharedTable* tab) {
+  *tab = SharedTable{nullptr, nullptr, 0};
+  if (job->per_latent) return GSWM_OK;
+  if (!d_workspace) return GSWM_E_WORKSPACE;
+  if (!aligned16(d_workspace)) return GSWM_E_ALIGN;
+  const size_t tiles = tiles_of(job->n_elems);
+  tab->table = reinterpret_cast<uint32_t*>(d_workspace);
+  tab->flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_workspace) + tiles * (size_t)kTileWords * 4);
+  tab->epoch = next_epoch();
+  return GSWM_OK;
+}
+
+static EmbedArgs make_embed_args(const gswm_job* job) {
   EmbedArgs a{};
   a.keys = job->d_keys;
   a.nonces = job->d_nonces;
   a.msgs = job->d_msgs;
-  a.table = reinterpret_cast<const uint32_t*>(d_workspace);
   a.n_elems = job->n_elems;
-  a.tiles_per_latent = (uint32_t)((job->n_elems + kTileElems - 1) / kTileElems);
   a.msg_words = (uint32_t)job->msg_bits / 32;
   a.tiled_words = (uint32_t)(job->n_elems / job->msg_bits) * a.msg_words;
   a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
@@ -475,7 +579,7 @@ int64_t gswm_launch_count(void) { return g_launches.load(std::memory_order_relax
 
 size_t gswm_workspace_bytes(const gswm_job* job) {
   if (!job || job->per_latent || job->n_elems <= 0) return 0;
-  return (size_t)(job->n_elems / 8);
+  return shared_workspace_bytes(job->n_elems);
 }
 
 int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int64_t n_streams,
@@ -501,15 +605,16 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
   if (rc) return rc;
   if (!d_out) return GSWM_E_NULL;
   if (!aligned16(d_out)) return GSWM_E_ALIGN;
+  if (offset >> 62) return GSWM_E_RANGE;
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!job->per_latent && (rc = launch_table(job, true, d_workspace, st))) return rc;
-  EmbedArgs a = make_embed_args(job, d_workspace);
+  EmbedArgs a = make_embed_args(job);
+  if ((rc = make_shared_table(job, d_workspace, &a.tab))) return rc;
   a.out = d_out;
   a.first_latent = first_latent;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
-  a.off_lo = (uint32_t)offset; a.off_hi = (uint32_t)(offset >> 32);
-  const unsigned grid = (unsigned)(job->n_latents * a.tiles_per_latent);
+  a.off_lo = (uint32_t)offset; a.off_hi = (uint32_t)(offset >> 32) << 2;
+  const dim3 grid((unsigned)job->n_latents, tiles_of(job->n_elems));
   if (job->per_latent) embed_kernel<true><<<grid, kThreads, 0, st>>>(a);
   else embed_kernel<false><<<grid, kThreads, 0, st>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -524,9 +629,9 @@ int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_la
   if (out_dtype != GSWM_F32 && out_dtype != GSWM_F64) return GSWM_E_DTYPE;
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!job->per_latent && (rc = launch_table(job, true, d_workspace, st))) return rc;
-  EmbedArgs a = make_embed_args(job, d_workspace);
-  const unsigned grid = (unsigned)(job->n_latents * a.tiles_per_latent);
+  EmbedArgs a = make_embed_args(job);
+  if ((rc = make_shared_table(job, d_workspace, &a.tab))) return rc;
+  const dim3 grid((unsigned)job->n_latents, tiles_of(job->n_elems));
   const int upl = u_per_latent ? 1 : 0;
   if (out_dtype == GSWM_F32) {
     if (job->per_latent) embed_injected_kernel<true, float><<<grid, kThreads, 0, st>>>(a, d_u, upl, (float*)d_out);
@@ -551,14 +656,13 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   if (job->msg_bits > 8192) return GSWM_E_RANGE;
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!job->per_latent && (rc = launch_table(job, false, d_workspace, st))) return rc;
   ExtractArgs a{};
+  if ((rc = make_shared_table(job, d_workspace, &a.tab))) return rc;
   a.keys = job->d_keys; a.nonces = job->d_nonces; a.msgs = job->d_msgs;
-  a.table = reinterpret_cast<const uint32_t*>(d_workspace);
   a.z = d_z; a.msg_out = d_msg_out; a.counts = d_counts; a.matched = d_matched;
   a.counters = reinterpret_cast<unsigned long long*>(d_counters);
   a.n_elems = job->n_elems;
-  a.tiles_per_latent = (uint32_t)((job->n_elems + kTileElems - 1) / kTileElems);
+  a.tiles_per_latent = tiles_of(job->n_elems);
   a.msg_bits = (uint32_t)job->msg_bits;
   a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
   a.copies = (uint32_t)copies;

@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <math_constants.h>
 
 #include "gswm_coeffs.inc"
 
@@ -50,9 +51,13 @@ __device__ __forceinline__ void chacha20_block(const uint32_t (&key)[8], const u
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Takes the place of np.random.uniform at
 // gs_insert.py:62; restated for the oracle in oracle/gs_oracle.py:philox4x32.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#ifndef GSWM_PHILOX_ROUNDS
+#define GSWM_PHILOX_ROUNDS 10
+#endif
+template <int kRounds = GSWM_PHILOX_ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kRounds; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
     uint4 n;
@@ -68,16 +73,38 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
 }
 
 // ------------------------------------------------------------------------------------------------
-// fp32 half-normal quantile with the bucket fused in.
+// The product's uniform source ("gswm uniforms v2", restated in oracle/gs_oracle.py:gswm_uniform_grid).
 //
-//   w       raw 32-bit random word; the uniform is u = ((w >> 9) + 0.5) * 2^-23
-//   flip    0x00000000 if the bucket bit y is 1, 0xFFFFFFFF if y is 0
-//   returns Phi^-1((u + y) / 2)  =  +g(u) for y = 1,  -g(1 - u) for y = 0           (gs_insert.py:64)
+// Every element gets a 23-bit integer m; its uniform is
+//       u = v        if the element's bucket bit y is 1,        v = (m + 1/2) 2^-23
+//       u = 1 - v    if y is 0                                  (again a grid point: m -> ~m)
+// so that the reference's z = Phi^-1((u + y)/2) (gs_insert.py:64) is  +g(v)  resp.  -g(v)  with
+// g(v) = sqrt(2) erfinv(v) the half-normal quantile: both buckets share ONE positive evaluation and the
+// bucket only sets the sign.  (u is exactly uniform on the grid and independent of y either way, because
+// m -> ~m is a bijection of the grid.)  v = (2m+1) 2^-24 is exact in fp32, which keeps small |z|
+// accurate (rounding u breaks the 1e-6 tolerance otherwise).
 //
-// 1 - u is again on the grid (complement the 23 bits), so both buckets share one positive-half
-// evaluation and the sign is OR-ed in at the end.  v = (2m+1) 2^-24 is exact in fp32, which is what
-// keeps small |z| accurate (rounding u breaks the 1e-6 tolerance otherwise).
+// The m's come from Philox in groups: three Philox4x32 calls (384 bits) feed 16 elements -- the four
+// float4 a thread stores in one "super-iteration".  float4 k = 0..2 take the top 23 bits of call k's
+// four words; float4 3 is assembled from the otherwise unused low bytes of the three calls.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+// bit pattern of f = 1 + m 2^-23 from the top 23 bits of a word: one funnel shift drops the low 9 bits
+// and shifts the exponent 0x7F in from the top
+__device__ __forceinline__ uint32_t fbits_top23(uint32_t w) { return __funnelshift_r(w, 0x7Fu, 9); }
+
+// ... and from the low bytes of three words: m = a.b0 | b.b0 << 8 | (c.b0 & 0x7F) << 16
+__device__ __forceinline__ uint32_t fbits_low_bytes(uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t ab = prmt(a, b, 0x0040u);            // bytes: a.b0, b.b0, a.b0, a.b0
+  const uint32_t abc = prmt(ab, c, 0x0410u);          // bytes: a.b0, b.b0, c.b0, a.b0
+  return (abc & 0x007FFFFFu) | 0x3F800000u;
+}
+
 __device__ __forceinline__ float horner_central(float x) {
   const float c[] = {GSWM_HNQ_CENTRAL_COEFFS};
   float p = c[0];
@@ -105,69 +132,59 @@ __device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT
   return r;
 }
 
-// Front end shared by both branches: v = (2m+1) 2^-24 exactly, x = c + lg2((1 - v)(1 + v - 2^-24)).
-__device__ __forceinline__ void quantile_front(uint32_t w, uint32_t flip, float& v, float& x) {
-  // f = 1 + m 2^-23 with m = 23 random bits (complemented for bucket 0): one funnel shift drops the
-  // low 9 bits and shifts the exponent 0x7F in from the top.
-  const float f = __uint_as_float(__funnelshift_r(w ^ flip, 0x7Fu, 9));
-  v = f - __uint_as_float(0x3F7FFFFFu);                             // exact: f - (1 - 2^-24)
-  const float t = fmaf(-GSWM_HNQ_KSCALE, v, GSWM_HNQ_KSCALE);       // K (1 - v), K = 2^c
-  x = lg2_fast(t * f);
-}
-
-__device__ __forceinline__ float quantile_tail(float x) {           // x < XSPLIT, ~0.3 % of elements
+__device__ __forceinline__ float quantile_tail(float x) {           // x < XSPLIT, ~0.12 % of elements
   return horner_tail(sqrt_fast(GSWM_HNQ_CSHIFT - x) - GSWM_HNQ_S0);
 }
 
-__device__ __forceinline__ float apply_sign(float g, uint32_t flip) {
-  return __uint_as_float(__float_as_uint(g) | (flip & 0x80000000u));
+// One element: g(v) for f = 1 + m 2^-23 given as a bit pattern.
+//   v = f - (1 - 2^-24) (exact),  x = c + lg2((1 - v)(1 + v - 2^-24)),  g = v P(x)  |  Q(sqrt(c - x))
+__device__ __forceinline__ float halfnormal_quantile(uint32_t fbits) {
+  const float f = __uint_as_float(fbits);
+  const float v = f - __uint_as_float(0x3F7FFFFFu);
+  const float t = fmaf(-GSWM_HNQ_KSCALE, v, GSWM_HNQ_KSCALE);
+  const float x = lg2_fast(t * f);
+  return (x >= GSWM_HNQ_XSPLIT) ? v * horner_central(x) : quantile_tail(x);
 }
 
-// One element (used by tests / small paths).
-__device__ __forceinline__ float bucket_quantile_f32(uint32_t w, uint32_t flip) {
-  float v, x;
-  quantile_front(w, flip, v, x);
-  const float g = (x >= GSWM_HNQ_XSPLIT) ? v * horner_central(x) : quantile_tail(x);
-  return apply_sign(g, flip);
+// Four elements as two packed pairs.  Blackwell's FFMA2 / FMUL2 / FADD2 (fma.rn.f32x2) do two fp32
+// operations per issued instruction.  The central polynomial is evaluated unconditionally for all four
+// elements and a single rarely-taken branch patches the elements that fell in the tail -- one
+// compare-and-branch per float4 instead of a divergence region per element.
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+
+__device__ __forceinline__ float2 horner_central2(float2 x) {
+  const float c[] = {GSWM_HNQ_CENTRAL_COEFFS};
+  float2 p = splat2(c[0]);
+#pragma unroll
+  for (int i = 1; i < (int)(sizeof(c) / sizeof(float)); ++i) p = __ffma2_rn(p, x, splat2(c[i]));
+  return p;
 }
 
-// Four elements at once: the central polynomial is evaluated unconditionally for all four, and a
-// single rarely-taken branch patches the elements that fell in the tail -- one compare-and-branch
-// per float4 instead of a divergence region per element.
-__device__ __forceinline__ float4 bucket_quantile4_f32(uint4 w, uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
-  float v0, v1, v2, v3, x0, x1, x2, x3;
-  quantile_front(w.x, f0, v0, x0);
-  quantile_front(w.y, f1, v1, x1);
-  quantile_front(w.z, f2, v2, x2);
-  quantile_front(w.w, f3, v3, x3);
-  float g0 = v0 * horner_central(x0);
-  float g1 = v1 * horner_central(x1);
-  float g2 = v2 * horner_central(x2);
-  float g3 = v3 * horner_central(x3);
-  if (fminf(fminf(x0, x1), fminf(x2, x3)) < GSWM_HNQ_XSPLIT) {
-    if (x0 < GSWM_HNQ_XSPLIT) g0 = quantile_tail(x0);
-    if (x1 < GSWM_HNQ_XSPLIT) g1 = quantile_tail(x1);
-    if (x2 < GSWM_HNQ_XSPLIT) g2 = quantile_tail(x2);
-    if (x3 < GSWM_HNQ_XSPLIT) g3 = quantile_tail(x3);
+__device__ __forceinline__ void quantile_front2(uint32_t fa, uint32_t fb, float2& v, float2& x) {
+  const float2 f = make_float2(__uint_as_float(fa), __uint_as_float(fb));
+  v = __fadd2_rn(f, splat2(-__uint_as_float(0x3F7FFFFFu)));
+  const float2 t = __ffma2_rn(v, splat2(-GSWM_HNQ_KSCALE), splat2(GSWM_HNQ_KSCALE));
+  const float2 q = __fmul2_rn(t, f);
+  x.x = lg2_fast(q.x);
+  x.y = lg2_fast(q.y);
+}
+
+// |z| of four elements from their f bit patterns; `sgn` (+-1 per element: +1 for bucket bit 1) gives z.
+__device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, float4 sgn) {
+  float2 v01, v23, x01, x23;
+  quantile_front2(f0, f1, v01, x01);
+  quantile_front2(f2, f3, v23, x23);
+  float2 g01 = __fmul2_rn(v01, horner_central2(x01));
+  float2 g23 = __fmul2_rn(v23, horner_central2(x23));
+  if (fminf(fminf(x01.x, x01.y), fminf(x23.x, x23.y)) < GSWM_HNQ_XSPLIT) {
+    if (x01.x < GSWM_HNQ_XSPLIT) g01.x = quantile_tail(x01.x);
+    if (x01.y < GSWM_HNQ_XSPLIT) g01.y = quantile_tail(x01.y);
+    if (x23.x < GSWM_HNQ_XSPLIT) g23.x = quantile_tail(x23.x);
+    if (x23.y < GSWM_HNQ_XSPLIT) g23.y = quantile_tail(x23.y);
   }
-  return make_float4(apply_sign(g0, f0), apply_sign(g1, f1), apply_sign(g2, f2), apply_sign(g3, f3));
-}
-
-// Flip masks of four consecutive elements from their bucket-bit nibble (bit 3 = first element):
-// spread the nibble to bit 7 of each byte lane with one multiply, then PRMT in sign-replicate mode
-// turns byte lane j into 0x00000000 / 0xFFFFFFFF.  flip = ~(bit ? ~0 : 0).
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
-__device__ __forceinline__ void nibble_flip_masks(uint32_t nib, uint32_t& f0, uint32_t& f1, uint32_t& f2, uint32_t& f3) {
-  // bit k of nib -> bit 7 of byte lane k ; inverted so that a SET bucket bit gives flip = 0
-  const uint32_t lanes = ~((nib & 0xFu) * (0x00204081u << 7)) & 0x80808080u;
-  f0 = prmt(lanes, 0u, 0xBBBBu);   // element 0 = nibble bit 3 = byte lane 3, sign-replicated
-  f1 = prmt(lanes, 0u, 0xAAAAu);
-  f2 = prmt(lanes, 0u, 0x9999u);
-  f3 = prmt(lanes, 0u, 0x8888u);
+  g01 = __fmul2_rn(g01, make_float2(sgn.x, sgn.y));
+  g23 = __fmul2_rn(g23, make_float2(sgn.z, sgn.w));
+  return make_float4(g01.x, g01.y, g23.x, g23.y);
 }
 
 // ------------------------------------------------------------------------------------------------

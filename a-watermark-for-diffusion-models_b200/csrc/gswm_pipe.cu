@@ -27,7 +27,7 @@ struct Slot {
   uint8_t* d_keys = nullptr;   // chunk * 32
   uint8_t* d_nonces = nullptr; // chunk * 16
   uint8_t* d_msgs = nullptr;   // chunk * kMaxMsgBytes
-  void* d_ws = nullptr;        // max_elems / 8
+  void* d_ws = nullptr;        // gswm_workspace_bytes for max_elems
   uint8_t* d_msg_out = nullptr;   // chunk * kMaxMsgBytes
   uint16_t* d_counts = nullptr;   // chunk * 8192
   int32_t* d_matched = nullptr;   // chunk
@@ -104,6 +104,9 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
   p->max_elems = max_elems;
   p->chunk = max_latents_per_chunk;
   const size_t lat_bytes = (size_t)p->chunk * (size_t)max_elems * 8;
+  gswm_job probe{};
+  probe.n_elems = max_elems;
+  const size_t ws_bytes = gswm_workspace_bytes(&probe);
   int rc = 0;
   auto A = [&](void** ptr, size_t bytes) {
     if (rc == 0) rc = (int)cudaMalloc(ptr, bytes);
@@ -115,7 +118,7 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
     A((void**)&s.d_keys, (size_t)p->chunk * 32);
     A((void**)&s.d_nonces, (size_t)p->chunk * 16);
     A((void**)&s.d_msgs, (size_t)p->chunk * kMaxMsgBytes);
-    A(&s.d_ws, (size_t)max_elems / 8);
+    A(&s.d_ws, ws_bytes);
     A((void**)&s.d_msg_out, (size_t)p->chunk * kMaxMsgBytes);
     A((void**)&s.d_counts, (size_t)p->chunk * 8192 * sizeof(uint16_t));
     A((void**)&s.d_matched, (size_t)p->chunk * sizeof(int32_t));

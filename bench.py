@@ -38,7 +38,7 @@ FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="latents per GPU per step")
@@ -148,7 +148,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -258,13 +258,22 @@ def run_gpu_arm(args):
         gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
         if ev:
             ev[1].record(stream)
-        counters.zero_()
         gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
                                          counters.data_ptr(), ws2p, sp), "gswm_extract")
         if ev:
             ev[2].record(stream)
         if world > 1:
-            dist.all_reduce(counters)                  # the only collective: 32 bytes of bit-match counters
+            # the only collective: 32 bytes of bit-match counters, all-reduced on a side stream so it overlaps the
+            # next step's embed (counters keep accumulating locally; `reduced` is the cross-rank total so far)
+            done.record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                reduced.copy_(counters)
+                dist.all_reduce(reduced)
+
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    done = torch.cuda.Event()
+    reduced = torch.zeros_like(counters)
 
     def barrier():
         if world > 1:
@@ -292,8 +301,10 @@ def run_gpu_arm(args):
     total_ms = t_begin.elapsed_time(t_end)
     embed_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     extract_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    final = counters.cpu().numpy().tolist()
-    exact = final[2] == final[3] == B * world          # every message decodes exactly at sigma = 0.325
+    n_steps_total = max(3, args.warmup) + args.steps
+    final = (reduced if world > 1 else counters).cpu().numpy().tolist()   # accumulated over every step so far
+    # every message of every step decodes exactly at sigma = 0.325
+    exact = final[2] == final[3] == B * world * n_steps_total and final[0] == final[1] == B * world * L * n_steps_total
 
     tm = torch.tensor([total_ms, embed_ms, extract_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -323,7 +334,7 @@ def run_gpu_arm(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e_value = B * world * e2e_steps / e2e_s
-    e2e_ok = int(h_cnt[2]) == B
+    e2e_ok = int(h_cnt[2]) == B and int(h_cnt[0]) == B * L
     key_bytes = km.keys.nbytes + km.nonces.nbytes + (km.msgs.nbytes if km.msgs is not None else 0)
     chunks = (B + 255) // 256
     h2d = B * n * 4 + (key_bytes * (1 if km.per_latent else chunks)) * 2

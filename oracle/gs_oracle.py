@@ -211,8 +211,7 @@ def embed_scalar(message, key: bytes, nonce16: bytes, u, l_bits: int = 256) -> l
 
 # --------------------------------------------------------------------------
 # the product's counter-based uniform source (restated so the oracle can be fed
-# the identical u).  Philox4x32-10 (Salmon et al., SC'11); one call per group of
-# four consecutive elements of the flattened [sample][element] space.
+# the identical u).  Philox4x32-10 (Salmon et al., SC'11).
 # --------------------------------------------------------------------------
 _PHILOX_M0 = np.uint64(0xD2511F53)
 _PHILOX_M1 = np.uint64(0xCD9E8D57)
@@ -235,30 +234,61 @@ def philox4x32(ctr: np.ndarray, key, rounds: int = 10) -> np.ndarray:
     return np.stack(c, axis=1).astype(np.uint32)
 
 
-def gswm_uniform_words(seed: int, offset: int, first_elem: int, count: int) -> np.ndarray:
-    """Raw 32-bit words the kernels draw for global elements [first_elem, first_elem+count).
+GSWM_TILE = 16384          # elements per tile (32 ChaCha blocks) -- the kernels' unit of work
+GSWM_PHILOX_ROUNDS = 10
 
-    Global element index g = sample_index * N + e.  Group G = g // 4 is the Philox counter
-    (G_lo, G_hi, offset_lo, offset_hi), key = (seed_lo, seed_hi); word g % 4 of the output
-    belongs to element g.
+
+def gswm_uniform_ints(seed: int, offset: int, latent_index: int, n_elems: int,
+                      rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
+    """The 23-bit integer m of every element of one latent ("gswm uniforms v2", csrc/gswm_math.cuh).
+
+    The latent is cut into tiles of 16384 elements; a tile into 4 super-iterations of 256 lanes; lane `tid`
+    of super-iteration `s` owns the four float4 (16 elements) at within-tile float4 indices
+    (4s + k) * 256 + tid, k = 0..3.  Its Philox counter is
+        G = ((latent_index * tiles_per_latent + tile) * 4 + s) * 256 + tid
+    and three calls W_c = Philox4x32(ctr = (G_lo, G_hi, offset_lo, (offset_hi << 2) + c), key = seed), c = 0..2,
+    feed the 16 elements: float4 k < 3, element j: m = W_k[j] >> 9; float4 3, element j:
+    m = (W_0[j] & 0xFF) | (W_1[j] & 0xFF) << 8 | (W_2[j] & 0x7F) << 16.
     """
-    g0 = first_elem // 4
-    g1 = (first_elem + count + 3) // 4
-    grp = np.arange(g0, g1, dtype=np.uint64)
-    ctr = np.empty((grp.size, 4), dtype=np.uint32)
-    ctr[:, 0] = (grp & np.uint64(0xFFFFFFFF)).astype(np.uint32)
-    ctr[:, 1] = (grp >> np.uint64(32)).astype(np.uint32)
+    tiles = (n_elems + GSWM_TILE - 1) // GSWM_TILE
+    t, s_, tid = np.meshgrid(np.arange(tiles, dtype=np.uint64), np.arange(4, dtype=np.uint64),
+                             np.arange(256, dtype=np.uint64), indexing="ij")
+    g = ((np.uint64(latent_index * tiles) + t) * np.uint64(4) + s_) * np.uint64(256) + tid      # (tiles, 4, 256)
+    g = g.reshape(-1)
+    ctr = np.empty((g.size, 4), dtype=np.uint32)
+    ctr[:, 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[:, 1] = (g >> np.uint64(32)).astype(np.uint32)
     ctr[:, 2] = offset & 0xFFFFFFFF
-    ctr[:, 3] = (offset >> 32) & 0xFFFFFFFF
-    w = philox4x32(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).reshape(-1)
-    lo = first_elem - 4 * g0
-    return w[lo:lo + count]
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    w = []
+    for c in range(3):
+        ctr[:, 3] = (((offset >> 32) << 2) + c) & 0xFFFFFFFF
+        w.append(philox4x32(ctr, key, rounds))                        # (tiles*1024, 4)
+    m = np.empty((tiles, 4, 4, 256, 4), dtype=np.uint32)            # [tile][s][k][tid][j]
+    for k in range(3):
+        m[:, :, k] = (w[k] >> np.uint32(9)).reshape(tiles, 4, 256, 4)
+    low = (w[0] & np.uint32(0xFF)) | ((w[1] & np.uint32(0xFF)) << np.uint32(8)) | ((w[2] & np.uint32(0x7F)) << np.uint32(16))
+    m[:, :, 3] = low.reshape(tiles, 4, 256, 4)
+    # element index within tile = 4 * ((4s + k) * 256 + tid) + j  ->  C order of [s][k][tid][j]
+    return m.reshape(-1)[:n_elems]
 
 
-def gswm_uniforms(seed: int, offset: int, first_elem: int, count: int) -> np.ndarray:
-    """float64 u in (0,1) exactly as the embed kernel defines it: ((w >> 9) + 0.5) * 2**-23."""
-    w = gswm_uniform_words(seed, offset, first_elem, count)
-    return ((w >> np.uint32(9)).astype(np.float64) + 0.5) * 2.0 ** -23
+def gswm_uniforms(seed: int, offset: int, latent_index: int, y: np.ndarray,
+                  rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
+    """float64 u in (0,1) for every element of one latent, given its bucket bits y:
+    v = (m + 1/2) 2^-23;  u = v where y == 1, u = 1 - v where y == 0 (both exact in float64)."""
+    y = np.asarray(y).reshape(-1)
+    m = gswm_uniform_ints(seed, offset, latent_index, y.size, rounds)
+    v = (m.astype(np.float64) + 0.5) * 2.0 ** -23
+    return np.where(y == 1, v, 1.0 - v)
+
+
+def embed_gswm(message, key: bytes, nonce16: bytes, seed: int, offset: int, latent_index: int, n_elems: int,
+               l_bits: int = 256, rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
+    """What gswm_embed must produce for one latent: the reference formula fed the product's uniforms."""
+    _, s_d = frame_message(message, n_elems, l_bits)
+    y = bucket_bits(s_d, key, nonce16)
+    return embed_from_uniform(y, gswm_uniforms(seed, offset, latent_index, y, rounds))
 
 
 # --------------------------------------------------------------------------

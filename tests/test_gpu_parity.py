@@ -83,7 +83,8 @@ def test_bucket_quantile_exhaustive(gswm, cuda_device, vec4):
             assert rc == 0
             torch.cuda.synchronize()
             got = d_o.cpu().numpy()
-            u = (m.astype(np.float64) + 0.5) * 2.0 ** -23
+            v = (m.astype(np.float64) + 0.5) * 2.0 ** -23
+            u = v if bucket else 1.0 - v                  # the kernel's uniform for bucket 0 is the complement
             ref = O.embed_from_uniform(np.full(u.shape, bucket), u)
             assert np.array_equal(got >= 0, ref >= 0), "bucket membership must be bit-exact"
             assert np.array_equal(got >= 0, np.full(u.shape, bool(bucket)))
@@ -117,8 +118,7 @@ def oracle_embed_batch(messages, keys, nonces, n, L, seed, offset, first_latent,
         k = keys[i] if isinstance(keys, list) else keys
         no = nonces[i] if isinstance(nonces, list) else nonces
         m = messages[i] if isinstance(messages, list) else messages
-        u = O.gswm_uniforms(seed, offset, (first_latent + i) * n, n)
-        out[i] = O.embed(m, k, no, u, L)
+        out[i] = O.embed_gswm(m, k, no, seed, offset, first_latent + i, n, L)
     return out
 
 
@@ -126,7 +126,7 @@ def oracle_embed_batch(messages, keys, nonces, n, L, seed, offset, first_latent,
                                      ((4, 64, 64), 1024), ((4, 72, 64), 512), ((4, 160, 128), 320)])
 def test_embed_shared_key_vs_oracle(gswm, cuda_device, shape, L):
     n = int(np.prod(shape))
-    b, seed, offset, first = 5, 0x5EED, 3, 1000
+    b, seed, offset, first = 5, 0x5EED, (7 << 32) + 3, 1000
     msg = bytes(np.random.RandomState(L).randint(0, 256, size=L // 8).astype(np.uint8))
     km = gswm.KeyMaterial.make(KEY, NONCE, msg, L)
     z = gswm.embed_batch(b, shape, km, seed, offset, first, cuda_device).cpu().numpy().reshape(b, n)
@@ -385,7 +385,7 @@ def test_argument_errors(gswm, cuda_device):
     with pytest.raises(ValueError):
         gswm.embed_batch(1, (4, 5, 5), km, 0, device=cuda_device)          # not a multiple of 512
     with pytest.raises(ValueError):
-        gswm.extract_batch(torch.zeros((1, 4, 96, 64), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 1024))
+        gswm.extract_batch(torch.zeros((1, 4, 96, 64), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 640))
     lib = gswm._lib.lib()
     job = gswm._lib.Job(1, 16384, 256, 0, 1, 1, 1)
     assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -7              # misaligned key pointer

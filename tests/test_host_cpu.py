@@ -48,7 +48,7 @@ def test_abi_basics_without_gpu(gswm):
     for code in range(-7, 0):
         assert gswm._lib.strerror(code).startswith("gswm:")
     job = gswm._lib.Job(3, 16384, 256, 0, None, None, None)
-    assert lib.gswm_workspace_bytes(C.byref(job)) == 2048
+    assert lib.gswm_workspace_bytes(C.byref(job)) == 2048 + 16          # one tile of keystream + its ready flag
     job.per_latent = 1
     assert lib.gswm_workspace_bytes(C.byref(job)) == 0
     # argument validation happens before any CUDA call
@@ -142,7 +142,7 @@ lo, hi = shard_range(B, rank, world)
 counters = torch.zeros(4, dtype=torch.int64)
 zs = []
 for g in range(lo, hi):
-    z = O.embed(b'abcd', key, nonce, O.gswm_uniforms(seed, 0, g * n, n), L)
+    z = O.embed_gswm(b'abcd', key, nonce, seed, 0, g, n, L)
     zs.append(z)
     zn = z + 2.5 * np.random.RandomState(g).standard_normal(n)
     bits = O.recover_message_bits(np.clip(zn, None, 8.0), key, nonce, L)
@@ -164,7 +164,7 @@ dist.destroy_process_group()
     c = np.load(tmp_path / "c.npy")
     key, nonce = bytes.fromhex(O.DEFAULT_KEY_HEX), bytes.fromhex(O.DEFAULT_NONCE_HEX)
     B, n, L = 6, 512, 32
-    whole = np.stack([O.embed(b"abcd", key, nonce, O.gswm_uniforms(9, 0, g * n, n), L) for g in range(B)])
+    whole = np.stack([O.embed_gswm(b"abcd", key, nonce, 9, 0, g, n, L) for g in range(B)])
     assert np.array_equal(z, whole)
     tot = np.zeros(4, dtype=np.int64)
     for g in range(B):

@@ -190,9 +190,24 @@ def test_philox_known_answers():
     assert [hex(int(v)) for v in p] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
 
 
-def test_gswm_uniforms_are_offset_consistent():
-    a = O.gswm_uniforms(0x5EED, 0, 0, 4096)
-    b = O.gswm_uniforms(0x5EED, 0, 1000, 96)
-    assert np.array_equal(a[1000:1096], b)
-    assert a.min() > 0 and a.max() < 1
-    assert abs(a.mean() - 0.5) < 0.02
+def test_gswm_uniform_source():
+    m = O.gswm_uniform_ints(0x5EED, 0, 3, 16384)
+    assert m.dtype == np.uint32 and m.size == 16384 and int(m.max()) < (1 << 23)
+    # a shorter latent is NOT a prefix (the counter depends on tiles per latent) but is deterministic
+    assert np.array_equal(O.gswm_uniform_ints(0x5EED, 0, 3, 16384), m)
+    assert not np.array_equal(O.gswm_uniform_ints(0x5EED, 1, 3, 16384), m)
+    assert not np.array_equal(O.gswm_uniform_ints(0x5EED, 0, 4, 16384), m)
+    # all four float4 of a super-iteration come from different bits
+    assert len(np.unique(m[:64])) > 60
+    y = np.random.RandomState(0).randint(0, 2, size=16384)
+    u = O.gswm_uniforms(0x5EED, 0, 3, y)
+    assert u.min() > 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+    v = (m + 0.5) * 2.0 ** -23
+    assert np.array_equal(u[y == 1], v[y == 1]) and np.array_equal(u[y == 0], 1 - v[y == 0])
+    # uniformity of the 23-bit integers: chi-square over 256 buckets of the top byte
+    big = np.concatenate([O.gswm_uniform_ints(7, 0, i, 65536) for i in range(8)])
+    hist = np.bincount(big >> 15, minlength=256)
+    chi2 = ((hist - big.size / 256) ** 2 / (big.size / 256)).sum()
+    assert chi2 < 340          # 255 dof: P(chi2 > 340) ~ 3e-4
+    z = O.embed_gswm("lthero", KEY, NONCE, 0x5EED, 0, 0, 16384)
+    assert O.bits_to_bytes(O.recover_message_bits(z, KEY, NONCE, 256))[:6] == b"lthero"
