@@ -277,12 +277,19 @@ embed_injected_kernel(const EmbedArgs a, const double* __restrict__ u, int u_per
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: extract.  grid = n_latents CTAs (one latent each, looping over its tiles).
+// K3: extract.  Persistent grid (a few CTAs per SM); CTA c decodes latents c, c + grid, c + 2 grid, ...
 //   bit    <- z >= threshold                                             (extract.py:82-84)
 //   bit    ^= keystream bit                                              (extract.py:86-87)
 //   count  <- per message position over the R copies                     (extract.py:91-98)
 //   msg    <- count > R/2  (strict; tie -> 0)                            (extract.py:99)
 //   score  <- popc(~(msg ^ reference))                                   (extract.py:103-109)
+//
+// The latents are streamed HBM -> shared memory by the TMA engine (cp.async.bulk, 1-D, completion on
+// an mbarrier) in CHUNKS of 4096 elements through a kStages-deep ring, issued by one thread kStages-1
+// chunks ahead of the consumers -- across latent boundaries, so the memory system never drains while a
+// latent's vote is being finalised.  The 256 threads read their four 4-element groups of the chunk with
+// conflict-free 128-bit shared loads.
+//
 // Fast path (kPow2): msg_bits divides 1024, so a thread's four positions never change and the four
 // counts ride in one register as byte lanes.  General path: shared-memory atomics per set bit.
 // ------------------------------------------------------------------------------------------------
@@ -297,141 +304,257 @@ struct ExtractArgs {
   int32_t* matched;
   unsigned long long* counters;
   int64_t n_elems;
+  int64_t n_latents;
   uint32_t tiles_per_latent;
+  uint32_t chunks_per_latent;
   uint32_t msg_bits;
   uint32_t msg_stride_bytes;
   uint32_t copies;            // R = n_elems / msg_bits
+  uint32_t ks_cache_tiles;    // shared-key mode: tiles of keystream kept resident in shared memory (0 = restage per tile)
 };
+
+#ifndef GSWM_CHUNK
+#define GSWM_CHUNK 4096
+#endif
+#ifndef GSWM_EXTRACT_MINB
+#define GSWM_EXTRACT_MINB 4
+#endif
+constexpr int kChunkElems = GSWM_CHUNK;              // 4 (or 8) chunks per tile
+constexpr int kChunksPerTile = kTileElems / kChunkElems;
+#ifndef GSWM_STAGES
+#define GSWM_STAGES 2
+#endif
+constexpr int kStages = GSWM_STAGES;
+constexpr int kStageBytes = kChunkElems * 4;         // sized for fp32; fp16 / bf16 use half of it
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on `bar`; streaming data: evict-first in L2
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
 
 template <typename T>
-struct ZLoad;   // loads 4 consecutive elements as float4 from a 4-element-group index
-
+struct ZSmem;   // 4 consecutive elements (group g of a chunk) from the staged chunk, as float4
 template <>
-struct ZLoad<float> {
-  static __device__ __forceinline__ float4 ld(const void* base, size_t g) {
-    return __ldcs(reinterpret_cast<const float4*>(base) + g);
-  }
+struct ZSmem<float> {
+  static __device__ __forceinline__ float4 ld(const void* stage, uint32_t g) { return reinterpret_cast<const float4*>(stage)[g]; }
 };
 template <>
-struct ZLoad<__half> {
-  static __device__ __forceinline__ float4 ld(const void* base, size_t g) {
-    const uint2 r = __ldcs(reinterpret_cast<const uint2*>(base) + g);
+struct ZSmem<__half> {
+  static __device__ __forceinline__ float4 ld(const void* stage, uint32_t g) {
+    const uint2 r = reinterpret_cast<const uint2*>(stage)[g];
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
     return make_float4(a.x, a.y, b.x, b.y);
   }
 };
 template <>
-struct ZLoad<__nv_bfloat16> {
-  static __device__ __forceinline__ float4 ld(const void* base, size_t g) {
-    const uint2 r = __ldcs(reinterpret_cast<const uint2*>(base) + g);
+struct ZSmem<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld(const void* stage, uint32_t g) {
+    const uint2 r = reinterpret_cast<const uint2*>(stage)[g];
     // bf16 -> fp32 is a 16-bit left shift
     return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u),
                        __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xFFFF0000u));
   }
 };
 
-__device__ __forceinline__ uint32_t quantise_nibble(const float4 z, const float thr) {
-  // bits 3..0 = elements 0..3 (MSB-first, as the keystream nibble is laid out)
-  return (z.x >= thr ? 8u : 0u) | (z.y >= thr ? 4u : 0u) | (z.z >= thr ? 2u : 0u) | (z.w >= thr ? 1u : 0u);
+// Quantise four elements to a word with the NEGATED bit of element j in bit 7 of byte j.
+// bit = (z >= T), T = quantise_threshold() < 0 tiny.  z - T is >= +0 exactly when z >= T (the sum of two floats
+// is never rounded across zero, subnormals are kept, and an exact zero comes out as +0), so after one FADD the
+// reference's bit is simply the complement of the sign bit -- including -0.0 and the [T, 0) sliver, which
+// extract.py:83 maps to 1.  Three byte permutes then gather the four sign bytes.
+__device__ __forceinline__ uint32_t negated_bits_word(const float4 z) {
+  const float c = -quantise_threshold();
+  const uint32_t s0 = __float_as_uint(z.x + c), s1 = __float_as_uint(z.y + c);
+  const uint32_t s2 = __float_as_uint(z.z + c), s3 = __float_as_uint(z.w + c);
+  const uint32_t p01 = __byte_perm(s0, s1, 0x0073);    // bytes: s0.b3, s1.b3, -, -
+  const uint32_t p23 = __byte_perm(s2, s3, 0x0073);
+  return __byte_perm(p01, p23, 0x5410);                // bytes: s0.b3, s1.b3, s2.b3, s3.b3
 }
 
 template <typename T, bool kPerLatent, bool kPow2>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, GSWM_EXTRACT_MINB)
 extract_kernel(const ExtractArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* s_ks = smem;                       // kTileWords
-  uint32_t* s_cnt = smem + kTileWords;         // msg_bits counters
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* s_stage = smem_raw;                                              // kStages x kStageBytes
+  uint32_t* s_ks_all = reinterpret_cast<uint32_t*>(smem_raw + kStages * kStageBytes);  // max(1, ks_cache_tiles) x kTileWords
+  uint32_t* s_cnt = s_ks_all + (a.ks_cache_tiles ? a.ks_cache_tiles : 1u) * kTileWords;  // msg_bits counters
+  __shared__ __align__(8) uint64_t s_full[kStages];
   __shared__ int s_matched;
 
-  const int64_t latent = blockIdx.x;
-  const float thr = quantise_threshold();
-  const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
-  const size_t z_g0 = (size_t)latent * (size_t)(a.n_elems >> 2);
+  const uint32_t cpl = a.chunks_per_latent;
+  // byte * magic puts the thread's keystream nibble (MSB = element 0) on bit 7 of bytes 0..3; the other nibble's
+  // products land on bits that the 0x80808080 mask drops, and no two partial products share a bit (no carries).
+  //   even group (high nibble b7..b4): shifts 0, 9, 18, 27;   odd group (low nibble b3..b0): shifts 4, 13, 22, 31
+  const uint32_t spread_magic = (threadIdx.x & 1u) ? 0x80402010u : 0x08040201u;
+  // latents owned by this CTA: blockIdx.x + k * gridDim.x
+  const int64_t n_mine = a.n_latents > (int64_t)blockIdx.x ? (a.n_latents - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total_chunks = n_mine * cpl;
 
+  uint64_t policy = 0;
+  // producer (thread 0): issue flat chunk q of this CTA's sequence into ring slot q % kStages
+  auto issue = [&](int64_t q) {
+    if (q >= total_chunks) return;
+    const int64_t seq = q / cpl;
+    const uint32_t within = (uint32_t)(q - seq * cpl);
+    const int64_t latent = blockIdx.x + seq * (int64_t)gridDim.x;
+    const int64_t e0 = (int64_t)within * kChunkElems;
+    const int64_t rem = a.n_elems - e0;
+    const uint32_t bytes = (uint32_t)(rem < kChunkElems ? rem : kChunkElems) * (uint32_t)sizeof(T);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.z) + ((size_t)latent * (size_t)a.n_elems + (size_t)e0) * sizeof(T);
+    uint64_t* bar = &s_full[q % kStages];
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(s_stage + (size_t)(q % kStages) * kStageBytes, src, bytes, bar, policy);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int sidx = 0; sidx < kStages; ++sidx) mbar_init(&s_full[sidx], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    s_matched = 0;
+  }
   for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) s_cnt[p] = 0;
-  if (threadIdx.x == 0) s_matched = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int64_t q = 0; q < kStages - 1; ++q) issue(q);               // kStages-1 chunks in flight from the start
+  }
   if constexpr (!kPerLatent) {                  // the first CTAs each produce slices of the shared keystream
     for (uint32_t t = blockIdx.x; t < a.tiles_per_latent; t += gridDim.x)
       publish_shared_slice(a.tab, a.keys, a.nonces, nullptr, a.n_elems, t, 0, 0);
   }
 
-  uint32_t packed = 0;                          // kPow2: byte lane k = count of element (3-k)
-  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;      // spilled byte lanes (only for very large latents)
-  uint32_t iters_since_spill = 0;
+  if constexpr (!kPerLatent) {                  // a latent's whole keystream fits the cache: stage it once per CTA
+    for (uint32_t t = 0; t < a.ks_cache_tiles; ++t)
+      acquire_shared_slice(s_ks_all + t * kTileWords, a.tab, t, tile_words(a.n_elems, t));
+  }
 
-  for (uint32_t tile = 0; tile < a.tiles_per_latent; ++tile) {
-    const int64_t tile_base = (int64_t)tile * kTileElems;
-    const uint32_t words = tile_words(a.n_elems, tile);
-    const uint32_t n_f4 = words << 3;
-    __syncthreads();                            // previous tile's keystream no longer needed
-    if constexpr (kPerLatent) compute_private_slice(s_ks, a.keys, a.nonces, nullptr, latent, tile, words, 0, 0);
-    else acquire_shared_slice(s_ks, a.tab, tile, words);
-    const size_t zt = z_g0 + (size_t)(tile_base >> 2);
-#pragma unroll 4
-    for (uint32_t i = threadIdx.x; i < n_f4; i += kThreads) {
-      const float4 z = ZLoad<T>::ld(a.z, zt + i);
-      const uint32_t byte = s_bytes[i >> 1];
-      const uint32_t ksn = (i & 1u) ? byte : (byte >> 4);
-      const uint32_t d = (quantise_nibble(z, thr) ^ ksn) & 0xFu;   // decrypted bits of 4 positions
-      if constexpr (kPow2) {
-        packed += (d * 0x00204081u) & 0x01010101u;                 // bit k -> byte lane k
+  unsigned long long acc_matched = 0, acc_exact = 0, acc_msgs = 0;   // thread 0 only; flushed once per CTA
+
+  int64_t q = 0;                                 // flat chunk index
+  for (int64_t seq = 0; seq < n_mine; ++seq) {
+    const int64_t latent = blockIdx.x + seq * (int64_t)gridDim.x;
+    uint32_t packed = 0;                          // kPow2: byte lane k = count of element k
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;      // spilled byte lanes (only for very large latents)
+    uint32_t adds_since_spill = 0;
+
+    for (uint32_t within = 0; within < cpl; ++within, ++q) {
+      // every thread has finished chunk q-1 (barrier at the end of the previous iteration): refill its slot
+      if (threadIdx.x == 0) issue(q + kStages - 1);
+      const uint32_t tile = within / kChunksPerTile;
+      const uint32_t chunk_in_tile = within % kChunksPerTile;
+      const bool ks_resident = !kPerLatent && a.ks_cache_tiles != 0;
+      uint32_t* s_ks = ks_resident ? s_ks_all + tile * kTileWords : s_ks_all;
+      if (chunk_in_tile == 0 && !ks_resident) {   // new tile: stage its keystream (both paths end with a barrier)
+        const uint32_t words = tile_words(a.n_elems, tile);
+        if constexpr (kPerLatent) compute_private_slice(s_ks, a.keys, a.nonces, nullptr, latent, tile, words, 0, 0);
+        else acquire_shared_slice(s_ks, a.tab, tile, words);
+      }
+      const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
+      const int64_t e0 = (int64_t)within * kChunkElems;
+      const int64_t rem = a.n_elems - e0;
+      const uint32_t n_grp = (uint32_t)(rem < kChunkElems ? rem : kChunkElems) >> 2;   // multiple of 128
+      mbar_wait(&s_full[q % kStages], (uint32_t)((q / kStages) & 1));
+      const unsigned char* stage = s_stage + (size_t)(q % kStages) * kStageBytes;
+      // keystream nibble of group i of the tile lives in byte i>>1 (high nibble for even i); this thread's groups
+      // of the chunk are k*256 + tid, so the byte is a compile-time offset from a per-thread base and the nibble
+      // half never changes: one multiply spreads it to bit 7 of byte j for element j (see spread magic below).
+      const uint8_t* ks_base = s_bytes + chunk_in_tile * (kChunkElems / 8) + (threadIdx.x >> 1);
+      auto consume = [&](uint32_t k) {
+        const uint32_t g = k * kThreads + threadIdx.x;
+        const uint32_t nz = negated_bits_word(ZSmem<T>::ld(stage, g));
+        const uint32_t ks = (uint32_t)ks_base[k * (kThreads / 2)] * spread_magic;
+        const uint32_t d = ~(nz ^ ks) & 0x80808080u;                   // decrypted bit of element j in bit 7 of byte j
+        if constexpr (kPow2) {
+          packed += d >> 7;
+        } else {
+          const uint32_t pos = (uint32_t)((e0 + 4 * (int64_t)g) % a.msg_bits);
+          if (d & 0x00000080u) atomicAdd(&s_cnt[pos + 0], 1u);
+          if (d & 0x00008000u) atomicAdd(&s_cnt[pos + 1], 1u);
+          if (d & 0x00800000u) atomicAdd(&s_cnt[pos + 2], 1u);
+          if (d & 0x80000000u) atomicAdd(&s_cnt[pos + 3], 1u);
+        }
+      };
+      if (n_grp == kChunkElems / 4) {
+#pragma unroll
+        for (uint32_t k = 0; k < kChunkElems / 4 / kThreads; ++k) consume(k);
       } else {
-        const uint32_t pos = (uint32_t)((tile_base + 4 * (int64_t)i) % a.msg_bits);
-        if (d & 8u) atomicAdd(&s_cnt[pos + 0], 1u);
-        if (d & 4u) atomicAdd(&s_cnt[pos + 1], 1u);
-        if (d & 2u) atomicAdd(&s_cnt[pos + 2], 1u);
-        if (d & 1u) atomicAdd(&s_cnt[pos + 3], 1u);
+        for (uint32_t k = 0; k * kThreads + threadIdx.x < n_grp; ++k) consume(k);
       }
-    }
-    if constexpr (kPow2) {
-      iters_since_spill += kTileF4 / kThreads;                     // 16 iterations per tile
-      if (iters_since_spill > 255 - kTileF4 / kThreads) {          // byte lanes would overflow next tile
-        c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
-        packed = 0; iters_since_spill = 0;
+      if constexpr (kPow2) {
+        adds_since_spill += kChunkElems / 4 / kThreads;                // adds per chunk
+        if (adds_since_spill > 250) {                                  // byte lanes would overflow
+          c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
+          packed = 0; adds_since_spill = 0;
+        }
       }
+      __syncthreads();                            // chunk q fully consumed: its ring slot and s_ks may be reused
     }
-  }
-  if constexpr (kPow2) {
-    c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
-    const uint32_t pos = (4u * threadIdx.x) & (a.msg_bits - 1u);
-    atomicAdd(&s_cnt[pos + 0], c3);            // byte lane 3 = nibble bit 3 = element 0
-    atomicAdd(&s_cnt[pos + 1], c2);
-    atomicAdd(&s_cnt[pos + 2], c1);
-    atomicAdd(&s_cnt[pos + 3], c0);
-  }
-  __syncthreads();
 
-  // majority vote, pack MSB-first, score against the reference message
-  const uint8_t* ref = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
-  int my_matched = 0;
-  for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) {   // msg_bits % 32 == 0: whole warps
-    const uint32_t cnt = s_cnt[p];
-    if (a.counts) a.counts[latent * a.msg_bits + p] = (uint16_t)cnt;
-    const bool bit = 2u * cnt > a.copies;                            // count_1 > len(segments)/2
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);         // lane l = position 32w + l
-    // position l of the word -> byte l>>3, bit 7-(l&7): reverse all bits, then swap bytes back
-    const uint32_t word = __byte_perm(__brev(ballot), 0u, 0x0123);
-    if ((threadIdx.x & 31) == 0) {
-      reinterpret_cast<uint32_t*>(a.msg_out + latent * (int64_t)(a.msg_bits >> 3))[p >> 5] = word;
-      if (ref) my_matched += __popc(~(word ^ __ldg(reinterpret_cast<const uint32_t*>(ref) + (p >> 5))));
+    // ---- end of latent: majority vote, pack MSB-first, score against the reference message ----
+    if constexpr (kPow2) {
+      c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
+      const uint32_t pos = (4u * threadIdx.x) & (a.msg_bits - 1u);
+      atomicAdd(&s_cnt[pos + 0], c0);
+      atomicAdd(&s_cnt[pos + 1], c1);
+      atomicAdd(&s_cnt[pos + 2], c2);
+      atomicAdd(&s_cnt[pos + 3], c3);
+      __syncthreads();
     }
-  }
-  if (ref) {
-    if ((threadIdx.x & 31) == 0 && my_matched) atomicAdd(&s_matched, my_matched);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int m = s_matched;
-      if (a.matched) a.matched[latent] = m;
-      if (a.counters) {
-        atomicAdd(&a.counters[GSWM_CTR_MATCHED_BITS], (unsigned long long)m);
-        atomicAdd(&a.counters[GSWM_CTR_EXACT_MSGS], (unsigned long long)(m == (int)a.msg_bits));
+    const uint8_t* ref = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
+    int my_matched = 0;
+    for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) {   // msg_bits % 32 == 0: whole warps
+      const uint32_t cnt = s_cnt[p];
+      s_cnt[p] = 0;                                                    // ready for the next latent
+      if (a.counts) a.counts[latent * a.msg_bits + p] = (uint16_t)cnt;
+      const bool bit = 2u * cnt > a.copies;                            // count_1 > len(segments)/2
+      const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);         // lane l = position 32w + l
+      // position l of the word -> byte l>>3, bit 7-(l&7): reverse all bits, then swap bytes back
+      const uint32_t word = __byte_perm(__brev(ballot), 0u, 0x0123);
+      if ((threadIdx.x & 31) == 0) {
+        reinterpret_cast<uint32_t*>(a.msg_out + latent * (int64_t)(a.msg_bits >> 3))[p >> 5] = word;
+        if (ref) my_matched += __popc(~(word ^ __ldg(reinterpret_cast<const uint32_t*>(ref) + (p >> 5))));
       }
     }
+    if (ref) {
+      if ((threadIdx.x & 31) == 0 && my_matched) atomicAdd(&s_matched, my_matched);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int m = s_matched;
+        s_matched = 0;
+        if (a.matched) a.matched[latent] = m;
+        acc_matched += (unsigned long long)m;
+        acc_exact += (unsigned long long)(m == (int)a.msg_bits);
+      }
+    }
+    if (threadIdx.x == 0) ++acc_msgs;
+    __syncthreads();                              // s_cnt / s_matched reset visible before the next latent
   }
-  if (threadIdx.x == 0 && a.counters) {
-    atomicAdd(&a.counters[GSWM_CTR_TOTAL_BITS], (unsigned long long)a.msg_bits);
-    atomicAdd(&a.counters[GSWM_CTR_TOTAL_MSGS], 1ull);
+  if (threadIdx.x == 0 && a.counters && acc_msgs) {
+    if (a.msgs) {
+      atomicAdd(&a.counters[GSWM_CTR_MATCHED_BITS], acc_matched);
+      atomicAdd(&a.counters[GSWM_CTR_EXACT_MSGS], acc_exact);
+    }
+    atomicAdd(&a.counters[GSWM_CTR_TOTAL_BITS], acc_msgs * a.msg_bits);
+    atomicAdd(&a.counters[GSWM_CTR_TOTAL_MSGS], acc_msgs);
   }
 }
 
@@ -521,15 +644,29 @@ static EmbedArgs make_embed_args(const gswm_job* job) {
   return a;
 }
 
+template <typename K>
+static int launch_extract_kernel(K kernel, const ExtractArgs& a, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 0, per_sm = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem)) != cudaSuccess) return (int)e;
+  if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+  const int64_t resident = (int64_t)sms * per_sm;
+  const unsigned grid = (unsigned)(a.n_latents < resident ? a.n_latents : resident);
+  kernel<<<grid, kThreads, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
 template <typename T>
-static void launch_extract(const ExtractArgs& a, bool per_latent, bool pow2, unsigned grid, size_t smem, cudaStream_t st) {
+static int launch_extract(const ExtractArgs& a, bool per_latent, bool pow2, size_t smem, cudaStream_t st) {
   if (per_latent) {
-    if (pow2) extract_kernel<T, true, true><<<grid, kThreads, smem, st>>>(a);
-    else extract_kernel<T, true, false><<<grid, kThreads, smem, st>>>(a);
-  } else {
-    if (pow2) extract_kernel<T, false, true><<<grid, kThreads, smem, st>>>(a);
-    else extract_kernel<T, false, false><<<grid, kThreads, smem, st>>>(a);
+    if (pow2) return launch_extract_kernel(extract_kernel<T, true, true>, a, smem, st);
+    return launch_extract_kernel(extract_kernel<T, true, false>, a, smem, st);
   }
+  if (pow2) return launch_extract_kernel(extract_kernel<T, false, true>, a, smem, st);
+  return launch_extract_kernel(extract_kernel<T, false, false>, a, smem, st);
 }
 
 }  // namespace gswm
@@ -666,14 +803,17 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   a.msg_bits = (uint32_t)job->msg_bits;
   a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
   a.copies = (uint32_t)copies;
+  a.n_latents = job->n_latents;
+  a.chunks_per_latent = (uint32_t)((job->n_elems + kChunkElems - 1) / kChunkElems);
   const bool pow2 = (1024 % job->msg_bits) == 0;
-  const size_t smem = (size_t)(kTileWords + job->msg_bits) * sizeof(uint32_t);
-  const unsigned grid = (unsigned)job->n_latents;
-  if (z_dtype == GSWM_F32) launch_extract<float>(a, job->per_latent != 0, pow2, grid, smem, st);
-  else if (z_dtype == GSWM_F16) launch_extract<__half>(a, job->per_latent != 0, pow2, grid, smem, st);
-  else launch_extract<__nv_bfloat16>(a, job->per_latent != 0, pow2, grid, smem, st);
+  a.ks_cache_tiles = (!job->per_latent && a.tiles_per_latent <= 8) ? a.tiles_per_latent : 0;
+  const size_t smem = (size_t)kStages * kStageBytes +
+                      (size_t)((a.ks_cache_tiles ? a.ks_cache_tiles : 1u) * kTileWords + job->msg_bits) * sizeof(uint32_t);
+  if (z_dtype == GSWM_F32) rc = launch_extract<float>(a, job->per_latent != 0, pow2, smem, st);
+  else if (z_dtype == GSWM_F16) rc = launch_extract<__half>(a, job->per_latent != 0, pow2, smem, st);
+  else rc = launch_extract<__nv_bfloat16>(a, job->per_latent != 0, pow2, smem, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
+  return rc;
 }
 
 }  // extern "C"
