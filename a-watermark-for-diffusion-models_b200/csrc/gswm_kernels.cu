@@ -121,10 +121,13 @@ __device__ __forceinline__ void chacha_tile_lane(uint32_t* __restrict__ dst, con
   }
 }
 
-__device__ __forceinline__ uint32_t tile_words(int64_t n_elems, uint32_t tile) {
+// elements of tile `tile` of an n_elems-element latent (n_elems is a multiple of 4, not necessarily of the tile)
+__device__ __forceinline__ uint32_t tile_elems(int64_t n_elems, uint32_t tile) {
   const int64_t remain = n_elems - (int64_t)tile * kTileElems;
-  return (uint32_t)(remain < kTileElems ? remain : kTileElems) >> 5;     // multiple of 16
+  return (uint32_t)(remain < kTileElems ? remain : kTileElems);
 }
+// keystream words covering them (a trailing partial word / partial ChaCha block is computed whole)
+__device__ __forceinline__ uint32_t tile_words(int64_t n_elems, uint32_t tile) { return (tile_elems(n_elems, tile) + 31u) >> 5; }
 
 // Producer side (shared key): warp 0 writes slice `tile` of the table and publishes it.
 __device__ __forceinline__ void publish_shared_slice(const SharedTable& tab, const uint8_t* __restrict__ keys,
@@ -154,7 +157,7 @@ __device__ __forceinline__ void acquire_shared_slice(uint32_t* __restrict__ s_ks
   }
   __syncthreads();
   const uint4* src = reinterpret_cast<const uint4*>(tab.table + (size_t)tile * kTileWords);
-  if (threadIdx.x * 4 < words) reinterpret_cast<uint4*>(s_ks)[threadIdx.x] = __ldcg(src + threadIdx.x);
+  if (threadIdx.x * 4 < words) reinterpret_cast<uint4*>(s_ks)[threadIdx.x] = __ldcg(src + threadIdx.x);   // whole uint4s: buffers are tile-sized
   __syncthreads();
 }
 
@@ -218,7 +221,7 @@ embed_kernel(const EmbedArgs a) {
   const uint32_t tile = blockIdx.y;
   const int64_t tile_base = (int64_t)tile * kTileElems;
   const uint32_t words = tile_words(a.n_elems, tile);
-  const uint32_t n_f4 = words << 3;                                   // multiple of 128
+  const uint32_t n_f4 = tile_elems(a.n_elems, tile) >> 2;
   build_sign_lut(s_sign);
   embed_stage<kPerLatent>(s_ks, a, latent, tile, words);             // ends with __syncthreads()
 
@@ -264,7 +267,7 @@ embed_injected_kernel(const EmbedArgs a, const double* __restrict__ u, int u_per
   const uint32_t tile = blockIdx.y;
   const int64_t tile_base = (int64_t)tile * kTileElems;
   const uint32_t words = tile_words(a.n_elems, tile);
-  const uint32_t n_el = words << 5;
+  const uint32_t n_el = tile_elems(a.n_elems, tile);
   embed_stage<kPerLatent>(s_ks, a, latent, tile, words);
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
   const double* up = u + (u_per_latent ? latent * a.n_elems : 0) + tile_base;
@@ -471,7 +474,7 @@ extract_kernel(const ExtractArgs a) {
       const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
       const int64_t e0 = (int64_t)within * kChunkElems;
       const int64_t rem = a.n_elems - e0;
-      const uint32_t n_grp = (uint32_t)(rem < kChunkElems ? rem : kChunkElems) >> 2;   // multiple of 128
+      const uint32_t n_grp = (uint32_t)(rem < kChunkElems ? rem : kChunkElems) >> 2;   // multiple of 8 (msg_bits | n_elems)
       mbar_wait(&s_full[q % kStages], (uint32_t)((q / kStages) & 1));
       const unsigned char* stage = s_stage + (size_t)(q % kStages) * kStageBytes;
       // keystream nibble of group i of the tile lives in byte i>>1 (high nibble for even i); this thread's groups
@@ -590,7 +593,7 @@ static int check_job(const gswm_job* job, bool for_extract) {
   if (!for_extract && !job->d_msgs) return GSWM_E_NULL;
   if ((reinterpret_cast<uintptr_t>(job->d_keys) | reinterpret_cast<uintptr_t>(job->d_nonces) |
        reinterpret_cast<uintptr_t>(job->d_msgs)) & 3u) return GSWM_E_ALIGN;   // read as 32-bit words
-  if (job->n_latents < 0 || job->n_elems <= 0 || (job->n_elems % 512) != 0) return GSWM_E_SHAPE;
+  if (job->n_latents < 0 || job->n_elems <= 0 || (job->n_elems % 4) != 0) return GSWM_E_SHAPE;
   if (job->msg_bits <= 0 || (job->msg_bits % 32) != 0 || job->msg_bits > job->n_elems) return GSWM_E_MSGLEN;
   if (for_extract && (job->n_elems % job->msg_bits) != 0) return GSWM_E_MSGLEN;
   if (job->n_elems > ((int64_t)1 << 31)) return GSWM_E_RANGE;
@@ -681,7 +684,7 @@ const char* gswm_strerror(int code) {
   switch (code) {
     case GSWM_OK: return "success";
     case GSWM_E_NULL: return "gswm: a required pointer is NULL";
-    case GSWM_E_SHAPE: return "gswm: n_elems must be a positive multiple of 512 and n_latents >= 0";
+    case GSWM_E_SHAPE: return "gswm: n_elems must be a positive multiple of 4 and n_latents >= 0";
     case GSWM_E_MSGLEN: return "gswm: msg_bits must be a positive multiple of 32, <= n_elems (and divide it for extract)";
     case GSWM_E_DTYPE: return "gswm: unknown element type";
     case GSWM_E_RANGE: return "gswm: size out of range";

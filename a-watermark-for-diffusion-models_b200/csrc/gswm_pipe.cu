@@ -54,7 +54,7 @@ namespace {
 int check_host_job(const gswm_pipe* p, const gswm_host_job* j, bool need_msg) {
   if (!p || !j || !j->h_keys || !j->h_nonces) return GSWM_E_NULL;
   if (need_msg && !j->h_msgs) return GSWM_E_NULL;
-  if (j->n_latents < 0 || j->n_elems <= 0 || (j->n_elems % 512) != 0) return GSWM_E_SHAPE;
+  if (j->n_latents < 0 || j->n_elems <= 0 || (j->n_elems % 4) != 0) return GSWM_E_SHAPE;
   if (j->n_elems > p->max_elems) return GSWM_E_RANGE;
   if (j->msg_bits <= 0 || (j->msg_bits % 32) != 0 || j->msg_bits > j->n_elems) return GSWM_E_MSGLEN;
   if (j->msg_bits > kMaxMsgBytes * 8) return GSWM_E_RANGE;
@@ -96,7 +96,7 @@ extern "C" {
 int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max_latents_per_chunk) {
   if (!out) return GSWM_E_NULL;
   *out = nullptr;
-  if (max_elems <= 0 || (max_elems % 512) != 0 || max_latents_per_chunk <= 0) return GSWM_E_SHAPE;
+  if (max_elems <= 0 || (max_elems % 4) != 0 || max_latents_per_chunk <= 0) return GSWM_E_SHAPE;
   GSWM_CUDA(cudaSetDevice(device));
   gswm_pipe* p = new (std::nothrow) gswm_pipe();
   if (!p) return (int)cudaErrorMemoryAllocation;

@@ -1,0 +1,38 @@
+"""Shared host logic of the reference-named embed shims (gs_insert / webui / ComfyUI): draw the
+uniforms exactly where the reference draws them, run the float64 device path, append info_data.txt."""
+from __future__ import annotations
+
+from datetime import datetime
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import codec
+
+
+def draw_uniforms(n: int, seeded: bool, seed: Optional[int], copies: int = 1) -> np.ndarray:
+    """The reference's per-element ``u = np.random.uniform(0, 1)`` / ``rng.uniform(0, 1)`` draws
+    (gs_insert.py:62; nodes.py:52-53,114-117; v1.5.2:27,72-75), vectorised: the legacy MT19937 stream
+    yields the same values whether drawn one at a time or as an array."""
+    if seeded:
+        return np.random.RandomState(seed=seed).uniform(0, 1, size=n)
+    return np.random.uniform(0, 1, size=(copies, n)) if copies > 1 else np.random.uniform(0, 1, size=n)
+
+
+def embed_injected(u: np.ndarray, latent_shape: Sequence[int], key: bytes, nonce: bytes, k: bytes, msg_bits: int,
+                   n_latents: int, out_dtype: torch.dtype, device=None) -> torch.Tensor:
+    """z = norm.ppf((u + y) / 2) on the GPU in float64 for n_latents latents; returns a device tensor."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    km = codec.KeyMaterial.make(key, nonce, k, msg_bits)
+    return codec.embed_batch_injected(torch.from_numpy(np.ascontiguousarray(u)).to(dev), latent_shape, km, n_latents, out_dtype)
+
+
+def append_info(lines: Sequence[str], path: str = "info_data.txt") -> None:
+    """Append one record to ./info_data.txt the way every reference variant does (gs_insert.py:68-74)."""
+    current_time = datetime.now().strftime("%Y-%m-%d %H:%M:%S")
+    with open(path, "a") as f:
+        f.write(f"Time: {current_time}\n")
+        for ln in lines:
+            f.write(ln + "\n")
+        f.write("----------------------\n")

@@ -155,8 +155,8 @@ def _device(device) -> torch.device:
 
 def _n_elems(shape: Sequence[int]) -> int:
     n = int(np.prod(shape))
-    if n <= 0 or n % 512:
-        raise ValueError(f"latent size {tuple(shape)} must be a positive multiple of 512 elements")
+    if n <= 0 or n % 4:
+        raise ValueError(f"latent size {tuple(shape)} must be a positive multiple of 4 elements")
     return n
 
 

@@ -63,3 +63,39 @@ def calculate_bit_accuracy(original_message_hex, extracted_message_bin):
     reference_bits = reference_bits[:n]
     agree = sum(a == b for a, b in zip(reference_bits, extracted_message_bin[:n]))
     return reference_bits, agree / n
+
+
+def write_batch_info(result_file, args):
+    """extract.py:166-175: the header block of result.txt."""
+    from datetime import datetime
+
+    result_file.write("=" * 40 + "Batch Info" + "=" * 40 + "\n")
+    result_file.write(f"Time,{datetime.now().strftime('%Y-%m-%d %H:%M:%S')}\n")
+    for field in ("key_hex", "nonce_hex", "original_message_hex", "num_inference_steps", "scheduler"):
+        result_file.write(f"{field},{getattr(args, field)}\n")
+    result_file.write("=" * 40 + "Batch Start" + "=" * 40 + "\n")
+
+
+def evaluate_latents(names, reversed_latents, args, result_file=None):
+    """Batched form of the per-image loop in extract.process_single_directory (extract.py:134-163): decode every
+    inverted latent of ``reversed_latents`` [B, ...] in one launch and report like the reference does --
+    ``<name>, Bit Accuracy, <acc>`` per image, then ``Average Bit Accuracy, <mean>``.  Returns
+    (extracted bit strings, accuracies, average)."""
+    z = _as_tensor(reversed_latents)
+    z = z.reshape(z.shape[0], -1)
+    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        z = z.to(torch.float32)
+    msg_bits = int(args.message_length)
+    km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)
+    dev = z.device if z.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    res = codec.extract_batch(z.to(dev), km)
+    strings = res.bit_strings()
+    accs = [calculate_bit_accuracy(args.original_message_hex, s)[1] for s in strings]
+    avg = sum(accs) / len(accs) if accs else 0.0
+    if result_file is not None:
+        for name, acc in zip(names, accs):
+            result_file.write(f"{name}, Bit Accuracy, {acc}\n")
+        if accs:
+            result_file.write(f"Average Bit Accuracy, {avg}\n\n")
+            result_file.write("=" * 40 + "Batch End" + "=" * 40 + "\n")
+    return strings, accs, avg

@@ -32,7 +32,7 @@ extern "C" {
 enum {
   GSWM_OK = 0,
   GSWM_E_NULL = -1,        /* a required pointer is NULL */
-  GSWM_E_SHAPE = -2,       /* n_elems not a positive multiple of 512, or n_latents < 0 */
+  GSWM_E_SHAPE = -2,       /* n_elems not a positive multiple of 4, or n_latents < 0 */
   GSWM_E_MSGLEN = -3,      /* msg_bits not a positive multiple of 32, > n_elems, or (extract) not dividing n_elems */
   GSWM_E_DTYPE = -4,       /* unknown element type code */
   GSWM_E_RANGE = -5,       /* a size exceeds what the kernels index */

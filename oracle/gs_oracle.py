@@ -153,7 +153,7 @@ def frame_message(message, n_elems: int, l_bits: int = 256, use_repeat: bool = F
         k = pad_message(message, l_bits // 8)
     repeats = n_elems // l_bits
     s_d = k * repeats
-    s_d += b"\x00" * (n_elems // 8 - len(s_d))  # nodes.py:85-87, only the consumed part
+    s_d += b"\x00" * ((n_elems + 7) // 8 - len(s_d))  # nodes.py:85-87, only the consumed part
     return k, s_d
 
 
@@ -192,7 +192,7 @@ def embed(message, key: bytes, nonce16: bytes, u: np.ndarray, l_bits: int = 256,
     """Whole embed for one latent; ``u`` is the flat float64 uniform stream (length N)."""
     n = int(np.asarray(u).size)
     _, s_d = frame_message(message, n, l_bits, use_repeat)
-    y = bucket_bits(s_d, key, nonce16, keystream)
+    y = bucket_bits(s_d, key, nonce16, keystream)[:n]               # the reference loop stops at N (nodes.py:122-123)
     return embed_from_uniform(y, np.asarray(u).reshape(-1))
 
 
@@ -287,7 +287,7 @@ def embed_gswm(message, key: bytes, nonce16: bytes, seed: int, offset: int, late
                l_bits: int = 256, rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
     """What gswm_embed must produce for one latent: the reference formula fed the product's uniforms."""
     _, s_d = frame_message(message, n_elems, l_bits)
-    y = bucket_bits(s_d, key, nonce16)
+    y = bucket_bits(s_d, key, nonce16)[:n_elems]
     return embed_from_uniform(y, gswm_uniforms(seed, offset, latent_index, y, rounds))
 
 

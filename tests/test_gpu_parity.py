@@ -123,7 +123,8 @@ def oracle_embed_batch(messages, keys, nonces, n, L, seed, offset, first_latent,
 
 
 @pytest.mark.parametrize("shape,L", [((4, 64, 64), 256), ((4, 128, 128), 256), ((4, 96, 64), 96), ((4, 8, 16), 32),
-                                     ((4, 64, 64), 1024), ((4, 72, 64), 512), ((4, 160, 128), 320)])
+                                     ((4, 64, 64), 1024), ((4, 72, 64), 512), ((4, 160, 128), 320), ((4, 8, 8), 32),
+                                     ((4, 152, 104), 256), ((4, 9, 9), 32), ((4, 72, 72), 1024)])
 def test_embed_shared_key_vs_oracle(gswm, cuda_device, shape, L):
     n = int(np.prod(shape))
     b, seed, offset, first = 5, 0x5EED, (7 << 32) + 3, 1000
@@ -213,7 +214,8 @@ def test_extract_golden_strings(gswm, cuda_device, golden, golden_arrays):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape,L", [((4, 64, 64), 256), ((4, 128, 128), 256), ((4, 64, 64), 32), ((4, 128, 128), 1024),
-                                     ((4, 96, 64), 96), ((4, 8, 16), 512), ((4, 64, 64), 2048), ((4, 160, 128), 320)])
+                                     ((4, 96, 64), 96), ((4, 8, 16), 512), ((4, 64, 64), 2048), ((4, 160, 128), 320),
+                                     ((4, 8, 8), 32), ((4, 152, 104), 256), ((4, 72, 72), 64)])
 def test_extract_counts_vs_oracle(gswm, cuda_device, dtype, shape, L):
     n = int(np.prod(shape))
     b = 6
@@ -380,10 +382,72 @@ def test_dropin_gs_insert_and_extract(gswm, cuda_device, golden, golden_arrays, 
     assert batch.shape == (5, 4, 64, 64) and batch.is_cuda
 
 
+def test_dropin_comfy_and_webui(gswm, cuda_device, golden, golden_arrays, tmp_path, monkeypatch):
+    """ComfyUI node function / GSLatent node and both webui scripts against the vectors the reference produced."""
+    import io
+
+    from gswm import comfy_nodes as cn
+    from gswm import extract as gx
+    from gswm import webui_v152 as w5
+    from gswm import webui_v160 as w6
+
+    monkeypatch.chdir(tmp_path)
+    for c in golden["embed_comfy"]:
+        z = cn.gs_watermark_init_noise(O.DEFAULT_KEY_HEX, O.DEFAULT_NONCE_HEX, "cpu", c["message"], 1, c["seed"], c["width"],
+                                       c["height"], c["message_length"])
+        assert z.dtype == torch.float32 and not z.is_cuda and list(z.shape) == c["shape"], c["name"]
+        zz = z.numpy().reshape(-1)
+        assert sha(np.packbits((zz >= 0).astype(np.uint8))) == c["sha256_signs"], c["name"]
+        assert rel_err(zz[:256], golden_arrays[c["name"] + "_z32_head"]).max() <= REL_TOL, c["name"]
+    lines = (tmp_path / "info_data.txt").read_text().splitlines()
+    assert lines[-9:] == golden["info_data_comfy_tail"][1:] and lines[-10].startswith("Time: ")
+    lat, first = cn.GSLatent().create_gs_latents(O.DEFAULT_KEY_HEX, O.DEFAULT_NONCE_HEX, "lthero", 3, 1, 42, 512, 512, 256)
+    assert list(lat["samples"].shape) == golden["gslatent_seeded"]["shape"]
+    assert torch.equal(lat["samples"][0], lat["samples"][2]) and torch.equal(first, lat["samples"][0])
+    np.random.seed(5)
+    lat2, _ = cn.GSLatent().create_gs_latents(O.DEFAULT_KEY_HEX, O.DEFAULT_NONCE_HEX, "lthero", 3, 0, 0, 512, 512, 256)
+    ref_u = np.random.RandomState(5).uniform(size=(3, 16384))
+    for b in range(3):
+        ref = O.embed("lthero", KEY, NONCE, ref_u[b], 256)
+        assert rel_err(lat2["samples"][b].numpy().reshape(-1), ref).max() <= REL_TOL
+    assert set(cn.NODE_CLASS_MAPPINGS) == {"Lthero_GSLatent", "Lthero_GS_KSamplerAdvanced"}
+
+    for c in golden["embed_webui"]:
+        for mod in (w5, w6):
+            w5.global_message, w5.global_key, w5.global_nonce = c["message"], O.DEFAULT_KEY_HEX, O.DEFAULT_NONCE_HEX
+            w5.global_use_randomSeed, w5.global_randomSeed, w5.global_use_repeat = 1, c["seed"], c["use_repeat"]
+            z = mod.init_gs_Z_s_T()
+            assert z.shape == (4, 64, 64) and z.dtype == np.float64
+            assert sha(np.packbits((z.reshape(-1) >= 0).astype(np.uint8))) == c["sha256_signs"], c["name"]
+            assert rel_err(z.reshape(-1)[:256], golden_arrays[c["name"] + "_z64_head"]).max() <= 1e-9
+    lines = (tmp_path / "info_data.txt").read_text().splitlines()
+    assert lines[-5:] == golden["info_data_webui_tail"][1:]
+    t = w5.advanced_creator((1, 4, 64, 64), [1])
+    assert t.shape == (1, 4, 64, 64) and t.dtype == torch.float32 and t.is_cuda
+    assert w6.global_randomSeed == w5.global_randomSeed
+
+    # batched evaluation front-end (extract.py:134-175)
+    base = torch.from_numpy(golden_arrays["cli_lthero_z32"])
+    batch = torch.stack([base, base + 4.3 * torch.randn(base.shape, generator=torch.Generator().manual_seed(1)),
+                         (base + 0.5 * torch.randn(base.shape, generator=torch.Generator().manual_seed(2)))]).clamp(max=8.0)
+    args = types.SimpleNamespace(key=KEY, nonce=NONCE, l=1, message_length=256, original_message_hex=(b"lthero" + bytes(26)).hex(),
+                                 key_hex=O.DEFAULT_KEY_HEX, nonce_hex=O.DEFAULT_NONCE_HEX, num_inference_steps=30, scheduler="DDIM")
+    buf = io.StringIO()
+    gx.write_batch_info(buf, args)
+    strings, accs, avg = gx.evaluate_latents(["a.png", "b.png", "c.png"], batch.half(), args, buf)
+    for i in range(3):
+        assert strings[i] == O.recover_message(batch[i].half().numpy(), KEY, NONCE, 256)
+        assert accs[i] == O.calculate_bit_accuracy(args.original_message_hex, strings[i])[1]
+    text = buf.getvalue().splitlines()
+    assert text[0] == "=" * 40 + "Batch Info" + "=" * 40 and text[2] == f"key_hex,{O.DEFAULT_KEY_HEX}"
+    assert text[8] == f"a.png, Bit Accuracy, {accs[0]}" and text[11] == f"Average Bit Accuracy, {avg}"
+    assert accs[0] == 1.0 and accs[2] == 1.0 and accs[1] < 1.0
+
+
 def test_argument_errors(gswm, cuda_device):
     km = gswm.KeyMaterial.make(KEY, NONCE, bytes(32), 256)
     with pytest.raises(ValueError):
-        gswm.embed_batch(1, (4, 5, 5), km, 0, device=cuda_device)          # not a multiple of 512
+        gswm.embed_batch(1, (3, 5, 5), km, 0, device=cuda_device)          # not a multiple of 4
     with pytest.raises(ValueError):
         gswm.extract_batch(torch.zeros((1, 4, 96, 64), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 640))
     lib = gswm._lib.lib()
@@ -391,7 +455,7 @@ def test_argument_errors(gswm, cuda_device):
     assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -7              # misaligned key pointer
     job = gswm._lib.Job(1, 16384, 250, 0, 16, 16, 16)
     assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -3
-    job = gswm._lib.Job(1, 1000, 32, 0, 16, 16, 16)
+    job = gswm._lib.Job(1, 1002, 32, 0, 16, 16, 16)
     assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -2
     assert lib.gswm_embed(None, 0, 0, 0, 16, 16, None) == -1
-    assert "multiple of 512" in gswm._lib.strerror(-2)
+    assert "multiple of 4" in gswm._lib.strerror(-2)

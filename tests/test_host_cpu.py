@@ -53,7 +53,7 @@ def test_abi_basics_without_gpu(gswm):
     assert lib.gswm_workspace_bytes(C.byref(job)) == 0
     # argument validation happens before any CUDA call
     assert lib.gswm_embed(None, 0, 0, 0, None, None, None) == -1
-    bad = gswm._lib.Job(1, 1000, 32, 0, 16, 16, 16)
+    bad = gswm._lib.Job(1, 1002, 32, 0, 16, 16, 16)
     assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, 16, None) == -2
     bad = gswm._lib.Job(1, 16384, 48, 0, 16, 16, 16)
     assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, 16, None) == -3
