@@ -94,9 +94,11 @@ int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int6
  * gs_insert.gs_watermark_init_noise's arithmetic (gs_insert.py:23-66; nodes.py:76-123) for a batch:
  * tile message, XOR ChaCha20 keystream, one uniform per element, z = Phi^-1((u + y) / 2), fp32 store.
  *
- * The uniform of global element g = (first_latent + b) * n_elems + e is
- *     u = ((w >> 9) + 0.5) * 2^-23,   w = word (g & 3) of Philox4x32-10(ctr = {g>>2, offset}, key = seed)
- * so a batch sharded over ranks by first_latent produces the same latents as one big batch.
+ * Uniform source ("gswm uniforms v2", csrc/gswm_math.cuh; restated in oracle/gs_oracle.py:gswm_uniform_ints): every
+ * element gets a 23-bit integer m from Philox4x32-10 keyed by `seed`, with the counter built from the GLOBAL
+ * latent index first_latent + b (so a batch sharded over ranks produces the same latents as one big batch),
+ * the tile, the position and `offset` (< 2^62).  v = (m + 1/2) 2^-23; u = v for bucket bit 1, u = 1 - v for
+ * bucket bit 0 (also a grid point), which makes z = +-sqrt(2) erfinv(v).
  * d_out: [n_latents][n_elems] fp32, 16-byte aligned.  d_workspace: gswm_workspace_bytes(job).
  */
 int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent,
