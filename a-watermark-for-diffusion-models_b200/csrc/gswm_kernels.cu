@@ -317,10 +317,10 @@ struct ExtractArgs {
 };
 
 #ifndef GSWM_CHUNK
-#define GSWM_CHUNK 4096
+#define GSWM_CHUNK 8192
 #endif
 #ifndef GSWM_EXTRACT_MINB
-#define GSWM_EXTRACT_MINB 4
+#define GSWM_EXTRACT_MINB 3
 #endif
 constexpr int kChunkElems = GSWM_CHUNK;              // 4 (or 8) chunks per tile
 constexpr int kChunksPerTile = kTileElems / kChunkElems;
@@ -355,44 +355,43 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uin
                ::"r"(smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
 }
 
+// Quantise the four elements of group g of a staged chunk to a word with the NEGATED reference bit of element j
+// in bit 7 of byte j.  The reference's bit is int(norm.cdf(z) * 2) == (z >= T), T = quantise_threshold() (tiny, < 0).
 template <typename T>
-struct ZSmem;   // 4 consecutive elements (group g of a chunk) from the staged chunk, as float4
+struct NegatedBits;
+
+// fp32: z - T is >= +0 exactly when z >= T (the sum of two floats is never rounded across zero, subnormals are
+// kept, an exact zero comes out as +0), so after one FADD the reference's bit is the complement of the sign bit --
+// including -0.0 and the [T, 0) sliver, which extract.py:83 maps to 1.  Three byte permutes gather the sign bytes.
 template <>
-struct ZSmem<float> {
-  static __device__ __forceinline__ float4 ld(const void* stage, uint32_t g) { return reinterpret_cast<const float4*>(stage)[g]; }
-};
-template <>
-struct ZSmem<__half> {
-  static __device__ __forceinline__ float4 ld(const void* stage, uint32_t g) {
-    const uint2 r = reinterpret_cast<const uint2*>(stage)[g];
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-  }
-};
-template <>
-struct ZSmem<__nv_bfloat16> {
-  static __device__ __forceinline__ float4 ld(const void* stage, uint32_t g) {
-    const uint2 r = reinterpret_cast<const uint2*>(stage)[g];
-    // bf16 -> fp32 is a 16-bit left shift
-    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u),
-                       __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xFFFF0000u));
+struct NegatedBits<float> {
+  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g) {
+    const float4 z = reinterpret_cast<const float4*>(stage)[g];
+    const float c = -quantise_threshold();
+    const uint32_t s0 = __float_as_uint(z.x + c), s1 = __float_as_uint(z.y + c);
+    const uint32_t s2 = __float_as_uint(z.z + c), s3 = __float_as_uint(z.w + c);
+    const uint32_t p01 = __byte_perm(s0, s1, 0x0073);    // bytes: s0.b3, s1.b3, -, -
+    const uint32_t p23 = __byte_perm(s2, s3, 0x0073);
+    return __byte_perm(p01, p23, 0x5410);                // bytes: s0.b3, s1.b3, s2.b3, s3.b3
   }
 };
 
-// Quantise four elements to a word with the NEGATED bit of element j in bit 7 of byte j.
-// bit = (z >= T), T = quantise_threshold() < 0 tiny.  z - T is >= +0 exactly when z >= T (the sum of two floats
-// is never rounded across zero, subnormals are kept, and an exact zero comes out as +0), so after one FADD the
-// reference's bit is simply the complement of the sign bit -- including -0.0 and the [T, 0) sliver, which
-// extract.py:83 maps to 1.  Three byte permutes then gather the four sign bytes.
-__device__ __forceinline__ uint32_t negated_bits_word(const float4 z) {
-  const float c = -quantise_threshold();
-  const uint32_t s0 = __float_as_uint(z.x + c), s1 = __float_as_uint(z.y + c);
-  const uint32_t s2 = __float_as_uint(z.z + c), s3 = __float_as_uint(z.w + c);
-  const uint32_t p01 = __byte_perm(s0, s1, 0x0073);    // bytes: s0.b3, s1.b3, -, -
-  const uint32_t p23 = __byte_perm(s2, s3, 0x0073);
-  return __byte_perm(p01, p23, 0x5410);                // bytes: s0.b3, s1.b3, s2.b3, s3.b3
-}
+// fp16 / bf16: no value of either type lies in [T, 0) except -0.0, so "z < T" is "sign set and magnitude non-zero".
+// Both types keep the sign in bit 15 and the magnitude in bits 14..0: (m + 0x7FFF) carries into bit 15 exactly when
+// the magnitude m is non-zero (no carry crosses the 16-bit lanes because m <= 0x7FFF).  One byte permute then puts
+// bit 15 / bit 31 of the two words onto bit 7 of bytes 0..3.
+struct NegatedBits16 {
+  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g) {
+    const uint2 r = reinterpret_cast<const uint2*>(stage)[g];
+    const uint32_t nx = ((r.x & 0x7FFF7FFFu) + 0x7FFF7FFFu) & r.x;   // bit 15 / 31: element is < 0 (and not -0.0)
+    const uint32_t ny = ((r.y & 0x7FFF7FFFu) + 0x7FFF7FFFu) & r.y;
+    return __byte_perm(nx, ny, 0x7531);                              // bytes: x.b1, x.b3, y.b1, y.b3
+  }
+};
+template <>
+struct NegatedBits<__half> : NegatedBits16 {};
+template <>
+struct NegatedBits<__nv_bfloat16> : NegatedBits16 {};
 
 template <typename T, bool kPerLatent, bool kPow2>
 __global__ void __launch_bounds__(kThreads, GSWM_EXTRACT_MINB)
@@ -483,7 +482,7 @@ extract_kernel(const ExtractArgs a) {
       const uint8_t* ks_base = s_bytes + chunk_in_tile * (kChunkElems / 8) + (threadIdx.x >> 1);
       auto consume = [&](uint32_t k) {
         const uint32_t g = k * kThreads + threadIdx.x;
-        const uint32_t nz = negated_bits_word(ZSmem<T>::ld(stage, g));
+        const uint32_t nz = NegatedBits<T>::word(stage, g);
         const uint32_t ks = (uint32_t)ks_base[k * (kThreads / 2)] * spread_magic;
         const uint32_t d = ~(nz ^ ks) & 0x80808080u;                   // decrypted bit of element j in bit 7 of byte j
         if constexpr (kPow2) {

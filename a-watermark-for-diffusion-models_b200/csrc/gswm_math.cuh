@@ -169,22 +169,56 @@ __device__ __forceinline__ void quantile_front2(uint32_t fa, uint32_t fb, float2
   x.y = lg2_fast(q.y);
 }
 
+// Scalar (one element per instruction) evaluation of the same thing; used for half of the elements when
+// GSWM_QUANTILE_MODE == 1 so that the FMA-heavy pipe (which also carries Philox's IMAD.WIDE) and the FMA-lite
+// pipe share the polynomial work.
+__device__ __forceinline__ void quantile_front1(uint32_t fa, float& v, float& x) {
+  const float f = __uint_as_float(fa);
+  v = f - __uint_as_float(0x3F7FFFFFu);
+  const float t = fmaf(-GSWM_HNQ_KSCALE, v, GSWM_HNQ_KSCALE);
+  x = lg2_fast(t * f);
+}
+
+#ifndef GSWM_QUANTILE_MODE
+#define GSWM_QUANTILE_MODE 0      // 0: both pairs packed (FFMA2); 1: pair 0 packed, pair 1 scalar; 2: all scalar
+#endif
+
 // |z| of four elements from their f bit patterns; `sgn` (+-1 per element: +1 for bucket bit 1) gives z.
 __device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, float4 sgn) {
-  float2 v01, v23, x01, x23;
+  float2 v01, v23, x01, x23, g01, g23;
+#if GSWM_QUANTILE_MODE == 2
+  quantile_front1(f0, v01.x, x01.x);
+  quantile_front1(f1, v01.y, x01.y);
+  g01 = make_float2(v01.x * horner_central(x01.x), v01.y * horner_central(x01.y));
+#else
   quantile_front2(f0, f1, v01, x01);
+  g01 = __fmul2_rn(v01, horner_central2(x01));
+#endif
+#if GSWM_QUANTILE_MODE >= 1
+  quantile_front1(f2, v23.x, x23.x);
+  quantile_front1(f3, v23.y, x23.y);
+  g23 = make_float2(v23.x * horner_central(x23.x), v23.y * horner_central(x23.y));
+#else
   quantile_front2(f2, f3, v23, x23);
-  float2 g01 = __fmul2_rn(v01, horner_central2(x01));
-  float2 g23 = __fmul2_rn(v23, horner_central2(x23));
+  g23 = __fmul2_rn(v23, horner_central2(x23));
+#endif
   if (fminf(fminf(x01.x, x01.y), fminf(x23.x, x23.y)) < GSWM_HNQ_XSPLIT) {
     if (x01.x < GSWM_HNQ_XSPLIT) g01.x = quantile_tail(x01.x);
     if (x01.y < GSWM_HNQ_XSPLIT) g01.y = quantile_tail(x01.y);
     if (x23.x < GSWM_HNQ_XSPLIT) g23.x = quantile_tail(x23.x);
     if (x23.y < GSWM_HNQ_XSPLIT) g23.y = quantile_tail(x23.y);
   }
+#if GSWM_QUANTILE_MODE == 2
+  return make_float4(g01.x * sgn.x, g01.y * sgn.y, g23.x * sgn.z, g23.y * sgn.w);
+#else
   g01 = __fmul2_rn(g01, make_float2(sgn.x, sgn.y));
+#if GSWM_QUANTILE_MODE == 1
+  return make_float4(g01.x, g01.y, g23.x * sgn.z, g23.y * sgn.w);
+#else
   g23 = __fmul2_rn(g23, make_float2(sgn.z, sgn.w));
   return make_float4(g01.x, g01.y, g23.x, g23.y);
+#endif
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

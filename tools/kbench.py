@@ -32,10 +32,19 @@ def main():
     key = bytes.fromhex("5822ff9cce6772f714192f43863f6bad1bf54b78326973897e6b66c3186b77a7")
     nonce = bytes.fromhex("05072fd1c2265f6f2e2a4080a2bfbdd8")
     msg = b"lthero" + bytes(26)
-    flat = torch.from_numpy(np.frombuffer(key + nonce + msg, np.uint8).copy()).to(dev)
-    job = _lib.Job(B, n, Lb, 0, flat.data_ptr(), flat.data_ptr() + 32, flat.data_ptr() + 48)
+    per = int(os.environ.get("KB_PER_LATENT", 0))
+    zdt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[os.environ.get("KB_ZDTYPE", "f32")]
+    zcode = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[zdt]
+    if per:
+        rs = np.random.RandomState(2025)
+        kb, nb, mb = rs.bytes(32 * B), rs.bytes(16 * B), rs.bytes(32 * B)
+        flat = torch.from_numpy(np.frombuffer(kb + nb + mb, np.uint8).copy()).to(dev)
+        job = _lib.Job(B, n, Lb, 1, flat.data_ptr(), flat.data_ptr() + 32 * B, flat.data_ptr() + 48 * B)
+    else:
+        flat = torch.from_numpy(np.frombuffer(key + nonce + msg, np.uint8).copy()).to(dev)
+        job = _lib.Job(B, n, Lb, 0, flat.data_ptr(), flat.data_ptr() + 32, flat.data_ptr() + 48)
     z = torch.empty((B, n), dtype=torch.float32, device=dev)
-    zn = torch.empty_like(z)
+    zn = torch.empty((B, n), dtype=zdt, device=dev)
     msgs = torch.empty((B, 32), dtype=torch.uint8, device=dev)
     matched = torch.empty((B,), dtype=torch.int32, device=dev)
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -51,14 +60,14 @@ def main():
             assert rc == 0, rc
 
         def extract():
-            rc = L.gswm_extract(C.byref(job), zn.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(), counters.data_ptr(),
+            rc = L.gswm_extract(C.byref(job), zn.data_ptr(), zcode, msgs.data_ptr(), None, matched.data_ptr(), counters.data_ptr(),
                                 ws2.data_ptr(), st)
             assert rc == 0, rc
 
         embed()
         torch.cuda.synchronize()
         zn.copy_(z + 0.325 * torch.randn_like(z))
-        res = {"lib": os.path.basename(path)}
+        res = {"lib": os.path.basename(path), "per_latent": per, "zdtype": str(zdt), "B": B, "n": n}
         for name, fn in (("embed_us", embed), ("extract_us", extract), ("pair_us", lambda: (embed(), extract()))):
             for _ in range(5):
                 fn()
@@ -79,7 +88,7 @@ def main():
         res["exact"] = counters.cpu().tolist()
         bytes_ = B * n * 4
         res["embed_GBps"] = round(bytes_ / res["embed_us"] / 1e3, 1)
-        res["extract_GBps"] = round(bytes_ / res["extract_us"] / 1e3, 1)
+        res["extract_GBps"] = round(B * n * zn.element_size() / res["extract_us"] / 1e3, 1)
         print(json.dumps(res), flush=True)
 
 
