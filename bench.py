@@ -284,7 +284,7 @@ def run_gpu_arm(args):
         step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
         sampler.start()
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -297,22 +297,29 @@ def run_gpu_arm(args):
     barrier()
     launches = gswm.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
-    # Second, instrumented pass over the same steps: events around every launch give each kernel's duration for the
-    # roofline block (kept out of the pass above so that event records do not sit between its launches).
-    inst_steps = min(args.steps, 200)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(inst_steps)]
-    barrier()
-    for k in range(inst_steps):
-        step(evs[k])
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    embed_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    extract_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    n_steps_total = max(3, args.warmup) + args.steps + inst_steps
+    if world > 1:
+        side.synchronize()
+    n_steps_total = max(3, args.warmup) + args.steps
     final = (reduced if world > 1 else counters).cpu().numpy().tolist()   # accumulated over every step so far
     # every message of every step decodes exactly at sigma = 0.325
     exact = final[2] == final[3] == B * world * n_steps_total and final[0] == final[1] == B * world * L * n_steps_total
-
+    # Per-kernel durations for the roofline block: the same launches, each kernel back to back `inst_steps` times
+    # between one pair of events (so no event record or dependent-launch gap sits inside the measured interval).
+    inst_steps = min(args.steps, 200)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    barrier()
+    ev[0].record(stream)
+    for k in range(inst_steps):
+        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
+    ev[1].record(stream)
+    for k in range(inst_steps):
+        gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
+                                         counters.data_ptr(), ws2p, sp), "gswm_extract")
+    ev[2].record(stream)
+    barrier()
+    embed_ms = ev[0].elapsed_time(ev[1]) / inst_steps
+    extract_ms = ev[1].elapsed_time(ev[2]) / inst_steps
+    clocks = sampler.stop() if rank == 0 else None
     tm = torch.tensor([total_ms, embed_ms, extract_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -393,7 +400,7 @@ def run_gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": workload_name(args), "latents_per_gpu": B, "latent_shape": [c, h, w], "msg_bits": L,
                    "l2": "inputs larger than L2 (2 x 268 MB streamed per step vs 126 MB L2)" if lat_bytes > 126e6 else
-                         "WARNING: working set fits L2", "timing": "CUDA events on the launch stream, max over ranks; per-kernel durations from a second, instrumented pass of %d steps" % inst_steps,
+                         "WARNING: working set fits L2", "timing": "CUDA events on the launch stream, max over ranks; per-kernel durations from %d back-to-back launches of each kernel between one event pair" % inst_steps,
                    "decode_exact": bool(exact), "counters": final},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
