@@ -1,11 +1,15 @@
 // Host-buffer layer of libgswm (gswm_pipe_*): streams batches that live in HOST memory through the
 // device kernels in chunks, two slots deep, so that the PCIe copy of one chunk overlaps the kernel
-// (and the opposite-direction copy) of the next.  This is the path a caller holding numpy / CPU
-// torch buffers takes -- the reference builds latents on the CPU and `.to(device)`s them
-// (README.md:112) and extract.py:70 returns a CPU tensor.
+// (and the copy) of the next.  This is the path a caller holding numpy / CPU torch buffers takes --
+// the reference builds latents on the CPU and `.to(device)`s them (README.md:112) and extract.py:70
+// returns a CPU tensor.
 //
-// Each slot owns one stream; everything for a chunk is enqueued in order on its slot's stream, so
-// buffer reuse two chunks later is ordered by the stream itself and no events are needed.
+// Each slot owns one stream; everything for a chunk is enqueued in order on its slot's stream, so device
+// buffer reuse two chunks later is ordered by the stream itself.  Nothing in the chunk loop blocks the
+// host: key material is uploaded once per call through a pinned staging buffer, and the small per-chunk
+// outputs (messages, counts, matched) land in per-slot pinned staging that is copied to the caller's
+// (possibly pageable) arrays when the slot comes round again.  The big latent buffers are copied
+// straight from / to the caller's memory: pinned memory there gives the full PCIe rate.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -22,15 +26,18 @@ constexpr int kMaxMsgBytes = 1024;   // msg_bits <= 8192
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;  // recorded after the chunk's last D2H
   void* d_in = nullptr;        // z (extract) or u (injected embed): chunk * max_elems * 8 bytes
   void* d_out = nullptr;       // latents out (embed): chunk * max_elems * 8 bytes
-  uint8_t* d_keys = nullptr;   // chunk * 32
-  uint8_t* d_nonces = nullptr; // chunk * 16
-  uint8_t* d_msgs = nullptr;   // chunk * kMaxMsgBytes
   void* d_ws = nullptr;        // gswm_workspace_bytes for max_elems
   uint8_t* d_msg_out = nullptr;   // chunk * kMaxMsgBytes
   uint16_t* d_counts = nullptr;   // chunk * 8192
   int32_t* d_matched = nullptr;   // chunk
+  uint8_t* h_msg_out = nullptr;   // pinned staging of the three outputs above
+  uint16_t* h_counts = nullptr;
+  int32_t* h_matched = nullptr;
+  // what the staging currently holds (to be delivered to the caller), -1 = nothing
+  int64_t pending_first = -1, pending_n = 0;
 };
 
 }  // namespace
@@ -41,6 +48,10 @@ struct gswm_pipe {
   int64_t chunk = 0;
   Slot slot[kSlots];
   int64_t* d_counters = nullptr;
+  // key material of the current call, uploaded once: [keys | nonces | msgs], grown on demand
+  uint8_t* d_km = nullptr;
+  uint8_t* h_km = nullptr;      // pinned staging
+  size_t km_capacity = 0;
 };
 
 namespace {
@@ -61,24 +72,53 @@ int check_host_job(const gswm_pipe* p, const gswm_host_job* j, bool need_msg) {
   return GSWM_OK;
 }
 
-// Upload the key material of latents [first, first + n) of a host job into a slot and describe it
-// as a device job.
-int stage_job(const gswm_host_job* hj, Slot& s, int64_t first, int64_t n, gswm_job* dj) {
+struct DeviceKeys {
+  const uint8_t* keys;
+  const uint8_t* nonces;
+  const uint8_t* msgs;   // null when the host job has no messages
+  int64_t msg_bytes;
+};
+
+// Upload the whole call's key material once (pinned staging -> device, on slot 0's stream; the other slots
+// wait for it through an event).
+int upload_keys(gswm_pipe* p, const gswm_host_job* hj, DeviceKeys* dk) {
+  const int64_t rows = hj->per_latent ? hj->n_latents : 1;
   const int64_t mb = hj->msg_bits / 8;
-  const int64_t rows = hj->per_latent ? n : 1;
+  const size_t need = (size_t)rows * (32 + 16 + (hj->h_msgs ? mb : 0));
+  if (need > p->km_capacity) {
+    if (p->d_km) cudaFree(p->d_km);
+    if (p->h_km) cudaFreeHost(p->h_km);
+    p->d_km = nullptr; p->h_km = nullptr; p->km_capacity = 0;
+    const size_t cap = std::max<size_t>(need, 1 << 16);
+    GSWM_CUDA(cudaMalloc((void**)&p->d_km, cap));
+    GSWM_CUDA(cudaMallocHost((void**)&p->h_km, cap));
+    p->km_capacity = cap;
+  }
+  std::memcpy(p->h_km, hj->h_keys, (size_t)rows * 32);
+  std::memcpy(p->h_km + rows * 32, hj->h_nonces, (size_t)rows * 16);
+  if (hj->h_msgs) std::memcpy(p->h_km + rows * 48, hj->h_msgs, (size_t)rows * mb);
+  GSWM_CUDA(cudaMemcpyAsync(p->d_km, p->h_km, need, cudaMemcpyHostToDevice, p->slot[0].stream));
+  cudaEvent_t up;
+  GSWM_CUDA(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
+  int rc = (int)cudaEventRecord(up, p->slot[0].stream);
+  for (int k = 1; k < kSlots && rc == 0; ++k) rc = (int)cudaStreamWaitEvent(p->slot[k].stream, up, 0);
+  cudaEventDestroy(up);
+  dk->keys = p->d_km;
+  dk->nonces = p->d_km + rows * 32;
+  dk->msgs = hj->h_msgs ? p->d_km + rows * 48 : nullptr;
+  dk->msg_bytes = mb;
+  return rc;
+}
+
+void chunk_job(const gswm_host_job* hj, const DeviceKeys& dk, int64_t first, int64_t n, gswm_job* dj) {
   const int64_t row0 = hj->per_latent ? first : 0;
-  GSWM_CUDA(cudaMemcpyAsync(s.d_keys, hj->h_keys + row0 * 32, rows * 32, cudaMemcpyHostToDevice, s.stream));
-  GSWM_CUDA(cudaMemcpyAsync(s.d_nonces, hj->h_nonces + row0 * 16, rows * 16, cudaMemcpyHostToDevice, s.stream));
-  if (hj->h_msgs)
-    GSWM_CUDA(cudaMemcpyAsync(s.d_msgs, hj->h_msgs + row0 * mb, rows * mb, cudaMemcpyHostToDevice, s.stream));
   dj->n_latents = n;
   dj->n_elems = hj->n_elems;
   dj->msg_bits = hj->msg_bits;
   dj->per_latent = hj->per_latent;
-  dj->d_keys = s.d_keys;
-  dj->d_nonces = s.d_nonces;
-  dj->d_msgs = hj->h_msgs ? s.d_msgs : nullptr;
-  return GSWM_OK;
+  dj->d_keys = dk.keys + row0 * 32;
+  dj->d_nonces = dk.nonces + row0 * 16;
+  dj->d_msgs = dk.msgs ? dk.msgs + row0 * dk.msg_bytes : nullptr;
 }
 
 int sync_all(gswm_pipe* p, int rc) {
@@ -87,6 +127,18 @@ int sync_all(gswm_pipe* p, int rc) {
     if (rc == 0 && e != cudaSuccess) rc = (int)e;
   }
   return rc;
+}
+
+// Deliver what a slot's pinned staging holds to the caller's arrays (after the slot's last copy finished).
+int drain_slot(Slot& s, int64_t msg_bytes, int64_t msg_bits, uint8_t* h_msg_out, uint16_t* h_counts, int32_t* h_matched) {
+  if (s.pending_first < 0) return GSWM_OK;
+  GSWM_CUDA(cudaEventSynchronize(s.done));
+  const int64_t f = s.pending_first, n = s.pending_n;
+  std::memcpy(h_msg_out + f * msg_bytes, s.h_msg_out, (size_t)(n * msg_bytes));
+  if (h_counts) std::memcpy(h_counts + f * msg_bits, s.h_counts, (size_t)(n * msg_bits) * sizeof(uint16_t));
+  if (h_matched) std::memcpy(h_matched + f, s.h_matched, (size_t)n * sizeof(int32_t));
+  s.pending_first = -1;
+  return GSWM_OK;
 }
 
 }  // namespace
@@ -111,17 +163,21 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
   auto A = [&](void** ptr, size_t bytes) {
     if (rc == 0) rc = (int)cudaMalloc(ptr, bytes);
   };
+  auto H = [&](void** ptr, size_t bytes) {
+    if (rc == 0) rc = (int)cudaMallocHost(ptr, bytes);
+  };
   for (auto& s : p->slot) {
     if (rc == 0) rc = (int)cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (rc == 0) rc = (int)cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     A(&s.d_in, lat_bytes);
     A(&s.d_out, lat_bytes);
-    A((void**)&s.d_keys, (size_t)p->chunk * 32);
-    A((void**)&s.d_nonces, (size_t)p->chunk * 16);
-    A((void**)&s.d_msgs, (size_t)p->chunk * kMaxMsgBytes);
     A(&s.d_ws, ws_bytes);
     A((void**)&s.d_msg_out, (size_t)p->chunk * kMaxMsgBytes);
     A((void**)&s.d_counts, (size_t)p->chunk * 8192 * sizeof(uint16_t));
     A((void**)&s.d_matched, (size_t)p->chunk * sizeof(int32_t));
+    H((void**)&s.h_msg_out, (size_t)p->chunk * kMaxMsgBytes);
+    H((void**)&s.h_counts, (size_t)p->chunk * 8192 * sizeof(uint16_t));
+    H((void**)&s.h_matched, (size_t)p->chunk * sizeof(int32_t));
   }
   A((void**)&p->d_counters, GSWM_N_COUNTERS * sizeof(int64_t));
   if (rc != 0) {
@@ -137,11 +193,14 @@ void gswm_pipe_destroy(gswm_pipe* p) {
   cudaSetDevice(p->device);
   for (auto& s : p->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_keys); cudaFree(s.d_nonces); cudaFree(s.d_msgs);
-    cudaFree(s.d_ws); cudaFree(s.d_msg_out); cudaFree(s.d_counts); cudaFree(s.d_matched);
+    cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_ws); cudaFree(s.d_msg_out); cudaFree(s.d_counts); cudaFree(s.d_matched);
+    cudaFreeHost(s.h_msg_out); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_matched);
+    if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   cudaFree(p->d_counters);
+  cudaFree(p->d_km);
+  cudaFreeHost(p->h_km);
   delete p;
 }
 
@@ -151,13 +210,15 @@ int gswm_pipe_embed(gswm_pipe* p, const gswm_host_job* job, uint64_t seed, uint6
   if (rc) return rc;
   if (!h_out) return GSWM_E_NULL;
   GSWM_CUDA(cudaSetDevice(p->device));
+  DeviceKeys dk;
+  if ((rc = upload_keys(p, job, &dk))) return sync_all(p, rc);
   const size_t row_bytes = (size_t)job->n_elems * sizeof(float);
   int c = 0;
   for (int64_t first = 0; first < job->n_latents && rc == 0; first += p->chunk, ++c) {
     Slot& s = p->slot[c % kSlots];
     const int64_t n = std::min(p->chunk, job->n_latents - first);
     gswm_job dj;
-    if ((rc = stage_job(job, s, first, n, &dj))) break;
+    chunk_job(job, dk, first, n, &dj);
     if ((rc = gswm_embed(&dj, seed, offset, first_latent + first, (float*)s.d_out, s.d_ws, s.stream))) break;
     rc = (int)cudaMemcpyAsync(reinterpret_cast<char*>(h_out) + (size_t)first * row_bytes, s.d_out, (size_t)n * row_bytes,
                               cudaMemcpyDeviceToHost, s.stream);
@@ -172,6 +233,8 @@ int gswm_pipe_embed_injected(gswm_pipe* p, const gswm_host_job* job, const doubl
   if (!h_out || !h_u) return GSWM_E_NULL;
   if (out_dtype != GSWM_F32 && out_dtype != GSWM_F64) return GSWM_E_DTYPE;
   GSWM_CUDA(cudaSetDevice(p->device));
+  DeviceKeys dk;
+  if ((rc = upload_keys(p, job, &dk))) return sync_all(p, rc);
   const size_t esz = out_dtype == GSWM_F32 ? 4 : 8;
   const size_t out_row = (size_t)job->n_elems * esz;
   const size_t u_row = (size_t)job->n_elems * sizeof(double);
@@ -180,7 +243,7 @@ int gswm_pipe_embed_injected(gswm_pipe* p, const gswm_host_job* job, const doubl
     Slot& s = p->slot[c % kSlots];
     const int64_t n = std::min(p->chunk, job->n_latents - first);
     gswm_job dj;
-    if ((rc = stage_job(job, s, first, n, &dj))) break;
+    chunk_job(job, dk, first, n, &dj);
     const char* u_src = reinterpret_cast<const char*>(h_u) + (u_per_latent ? (size_t)first * u_row : 0);
     if ((rc = (int)cudaMemcpyAsync(s.d_in, u_src, (u_per_latent ? (size_t)n : 1) * u_row, cudaMemcpyHostToDevice, s.stream))) break;
     if ((rc = gswm_embed_injected(&dj, (const double*)s.d_in, u_per_latent, s.d_out, out_dtype, s.d_ws, s.stream))) break;
@@ -200,34 +263,42 @@ int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, i
   GSWM_CUDA(cudaSetDevice(p->device));
   const size_t esz = z_dtype == GSWM_F32 ? 4 : 2;
   const size_t z_row = (size_t)job->n_elems * esz;
-  const size_t mb = (size_t)job->msg_bits / 8;
-  // counters are accumulated by both slots' kernels; zero them on slot 0 and make slot 1 wait for it
-  cudaEvent_t zeroed;
-  GSWM_CUDA(cudaEventCreateWithFlags(&zeroed, cudaEventDisableTiming));
+  const int64_t mb = job->msg_bits / 8;
+  const bool want_matched = h_matched && job->h_msgs;
+  // counters are accumulated by both slots' kernels: zero them (with the key upload) on slot 0's stream, which the
+  // other slots wait for inside upload_keys
   rc = (int)cudaMemsetAsync(p->d_counters, 0, GSWM_N_COUNTERS * sizeof(int64_t), p->slot[0].stream);
-  if (rc == 0) rc = (int)cudaEventRecord(zeroed, p->slot[0].stream);
-  for (int k = 1; k < kSlots && rc == 0; ++k) rc = (int)cudaStreamWaitEvent(p->slot[k].stream, zeroed, 0);
+  DeviceKeys dk{};
+  if (rc == 0) rc = upload_keys(p, job, &dk);
+  for (auto& s : p->slot) s.pending_first = -1;
   int c = 0;
   for (int64_t first = 0; first < job->n_latents && rc == 0; first += p->chunk, ++c) {
     Slot& s = p->slot[c % kSlots];
     const int64_t n = std::min(p->chunk, job->n_latents - first);
+    // the slot's staging still holds the outputs of chunk c - kSlots: hand them to the caller first
+    if ((rc = drain_slot(s, mb, job->msg_bits, h_msg_out, h_counts, want_matched ? h_matched : nullptr))) break;
     gswm_job dj;
-    if ((rc = stage_job(job, s, first, n, &dj))) break;
+    chunk_job(job, dk, first, n, &dj);
     if ((rc = (int)cudaMemcpyAsync(s.d_in, reinterpret_cast<const char*>(h_z) + (size_t)first * z_row, (size_t)n * z_row,
                                    cudaMemcpyHostToDevice, s.stream))) break;
     if ((rc = gswm_extract(&dj, s.d_in, z_dtype, s.d_msg_out, h_counts ? s.d_counts : nullptr,
-                           (h_matched && dj.d_msgs) ? s.d_matched : nullptr, p->d_counters, s.d_ws, s.stream))) break;
-    if ((rc = (int)cudaMemcpyAsync(h_msg_out + (size_t)first * mb, s.d_msg_out, (size_t)n * mb, cudaMemcpyDeviceToHost, s.stream))) break;
-    if (h_counts &&
-        (rc = (int)cudaMemcpyAsync(h_counts + (size_t)first * job->msg_bits, s.d_counts,
-                                   (size_t)n * job->msg_bits * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream))) break;
-    if (h_matched && dj.d_msgs &&
-        (rc = (int)cudaMemcpyAsync(h_matched + first, s.d_matched, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream))) break;
+                           want_matched ? s.d_matched : nullptr, p->d_counters, s.d_ws, s.stream))) break;
+    if ((rc = (int)cudaMemcpyAsync(s.h_msg_out, s.d_msg_out, (size_t)(n * mb), cudaMemcpyDeviceToHost, s.stream))) break;
+    if (h_counts && (rc = (int)cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)(n * job->msg_bits) * sizeof(uint16_t),
+                                               cudaMemcpyDeviceToHost, s.stream))) break;
+    if (want_matched && (rc = (int)cudaMemcpyAsync(s.h_matched, s.d_matched, (size_t)n * sizeof(int32_t),
+                                                   cudaMemcpyDeviceToHost, s.stream))) break;
+    if ((rc = (int)cudaEventRecord(s.done, s.stream))) break;
+    s.pending_first = first;
+    s.pending_n = n;
+  }
+  for (auto& s : p->slot) {
+    const int r2 = drain_slot(s, mb, job->msg_bits, h_msg_out, h_counts, want_matched ? h_matched : nullptr);
+    if (rc == 0) rc = r2;
   }
   rc = sync_all(p, rc);
   if (rc == 0 && h_counters)
     rc = (int)cudaMemcpy(h_counters, p->d_counters, GSWM_N_COUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost);
-  cudaEventDestroy(zeroed);
   return rc;
 }
 

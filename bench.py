@@ -360,8 +360,7 @@ def run_gpu_arm(args):
     # the embedded latents that came back over PCIe must be the ones the resident path produced
     e2e_ok = e2e_ok and bool(torch.equal(h_out[:8], z[:8].cpu()))
     key_bytes = km.keys.nbytes + km.nonces.nbytes + (km.msgs.nbytes if km.msgs is not None else 0)
-    chunks = (B + 255) // 256
-    h2d = B * n * 4 + (key_bytes * (1 if km.per_latent else chunks)) * 2
+    h2d = B * n * 4 + key_bytes * 2                  # latents in + key material once per pipe call
     d2h = B * n * 4 + B * (L // 8) + B * 4 + 32
     pipe_e.close()
     pipe_x.close()
