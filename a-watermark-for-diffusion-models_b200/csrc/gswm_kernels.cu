@@ -129,19 +129,28 @@ __device__ __forceinline__ uint32_t tile_elems(int64_t n_elems, uint32_t tile) {
 // keystream words covering them (a trailing partial word / partial ChaCha block is computed whole)
 __device__ __forceinline__ uint32_t tile_words(int64_t n_elems, uint32_t tile) { return (tile_elems(n_elems, tile) + 31u) >> 5; }
 
-// Producer side (shared key): warp 0 writes slice `tile` of the table and publishes it.
+// Producer side (shared key): the calling WARP (all 32 lanes) writes slice `tile` of the table and publishes it.
 __device__ __forceinline__ void publish_shared_slice(const SharedTable& tab, const uint8_t* __restrict__ keys,
                                                      const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
                                                      int64_t n_elems, uint32_t tile, uint32_t msg_words, uint32_t tiled_words) {
-  if (threadIdx.x < 32) {
-    if (threadIdx.x * 16 < tile_words(n_elems, tile))
-      chacha_tile_lane(tab.table + (size_t)tile * kTileWords, keys, nonces, msg, 0, tile, threadIdx.x, msg_words, tiled_words);
-    __threadfence();                                   // each lane's slice stores before the flag
-    __syncwarp();
-    if (threadIdx.x == 0) {
-      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(tab.flags + tile), "l"(tab.epoch) : "memory");
-    }
+  const uint32_t lane = threadIdx.x & 31u;
+  if (lane * 16 < tile_words(n_elems, tile))
+    chacha_tile_lane(tab.table + (size_t)tile * kTileWords, keys, nonces, msg, 0, tile, lane, msg_words, tiled_words);
+  __threadfence();                                     // each lane's slice stores before the flag
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(tab.flags + tile), "l"(tab.epoch) : "memory");
   }
+}
+
+// CTA 0 produces the whole table, warp w taking tiles w, w + 8, ...: the producer never waits on anything and is the
+// first CTA the hardware dispatches, so consumers spinning on a flag cannot deadlock.
+__device__ __forceinline__ void produce_shared_table(const SharedTable& tab, const uint8_t* __restrict__ keys,
+                                                     const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
+                                                     int64_t n_elems, uint32_t tiles, uint32_t msg_words, uint32_t tiled_words) {
+  if (blockIdx.x != 0) return;
+  for (uint32_t t = threadIdx.x >> 5; t < tiles; t += kThreads / 32)
+    publish_shared_slice(tab, keys, nonces, msg, n_elems, t, msg_words, tiled_words);
 }
 
 // Consumer side (shared key): wait for slice `tile`, copy it to shared memory (L2 loads: the producer ran on
@@ -185,21 +194,25 @@ struct EmbedArgs {
   SharedTable tab;           // shared-key bucket-bit table (keystream ^ tiled message)
   float* out;
   int64_t n_elems;
+  int64_t n_latents;
   int64_t first_latent;      // global index of latent 0 (sharding)
+  uint32_t tiles_per_latent;
   uint32_t msg_words;
   uint32_t tiled_words;
   uint32_t msg_stride_bytes;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;   // off_hi holds (offset_hi << 2): its low 2 bits select the Philox call
+  PhiloxKeys rk;             // round keys of (seed_lo, seed_hi)
 };
 
-// grid = (n_latents, tiles_per_latent): blockIdx.x = latent, blockIdx.y = tile.
+// Staging for the injected-uniform kernel, grid = (n_latents, tiles_per_latent): blockIdx.x = latent, blockIdx.y = tile.
 template <bool kPerLatent>
 __device__ __forceinline__ void embed_stage(uint32_t* s_ks, const EmbedArgs& a, int64_t latent, uint32_t tile, uint32_t words) {
   if constexpr (kPerLatent) {
     compute_private_slice(s_ks, a.keys, a.nonces, a.msgs + latent * (int64_t)a.msg_stride_bytes, latent, tile, words,
                           a.msg_words, a.tiled_words);
   } else {
-    if (blockIdx.x == 0) publish_shared_slice(a.tab, a.keys, a.nonces, a.msgs, a.n_elems, tile, a.msg_words, a.tiled_words);
+    if (blockIdx.x == 0 && threadIdx.x < 32)
+      publish_shared_slice(a.tab, a.keys, a.nonces, a.msgs, a.n_elems, tile, a.msg_words, a.tiled_words);
     acquire_shared_slice(s_ks, a.tab, tile, words);
   }
 }
@@ -212,49 +225,126 @@ __device__ __forceinline__ void build_sign_lut(float4* lut) {
   lut[2 * b + 1] = make_float4((b & 0x08u) ? 1.f : -1.f, (b & 0x04u) ? 1.f : -1.f, (b & 0x02u) ? 1.f : -1.f, (b & 0x01u) ? 1.f : -1.f);
 }
 
+#ifndef GSWM_PHILOX_CONST_KEYS
+#define GSWM_PHILOX_CONST_KEYS 1
+#endif
+#ifndef GSWM_EMIT_PAIRS
+#define GSWM_EMIT_PAIRS 0
+#endif
+// One SUPER-ITERATION of a tile: 1024 float4 = 4 per thread, fed by three Philox calls.
+// Philox counter word 0..1: G = ((global_latent * tiles + tile) * 4 + sidx) * 256 + tid; words 2..3: offset, call index.
+template <bool kGuard>
+__device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const uint8_t* __restrict__ s_bytes,
+                                                      const float4* __restrict__ my_sign, float4* __restrict__ out4,
+                                                      uint64_t g_tile, uint32_t sidx, uint32_t n_f4) {
+  const uint64_t g = g_tile + (uint64_t)sidx * kThreads;
+  const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
+#if GSWM_PHILOX_CONST_KEYS
+  const uint4 c0 = philox4x32_keys(make_uint4(glo, ghi, a.off_lo, a.off_hi + 0u), a.rk);
+  const uint4 c1 = philox4x32_keys(make_uint4(glo, ghi, a.off_lo, a.off_hi + 1u), a.rk);
+  const uint4 c2 = philox4x32_keys(make_uint4(glo, ghi, a.off_lo, a.off_hi + 2u), a.rk);
+#else
+  const uint4 c0 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 0u), a.seed_lo, a.seed_hi);
+  const uint4 c1 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 1u), a.seed_lo, a.seed_hi);
+  const uint4 c2 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 2u), a.seed_lo, a.seed_hi);
+#endif
+  const uint32_t i0 = (4u * sidx) * kThreads + threadIdx.x;
+  const uint32_t f0[4] = {fbits_top23(c0.x), fbits_top23(c0.y), fbits_top23(c0.z), fbits_top23(c0.w)};
+  const uint32_t f1[4] = {fbits_top23(c1.x), fbits_top23(c1.y), fbits_top23(c1.z), fbits_top23(c1.w)};
+  const uint32_t f2[4] = {fbits_top23(c2.x), fbits_top23(c2.y), fbits_top23(c2.z), fbits_top23(c2.w)};
+  const uint32_t f3[4] = {fbits_low_bytes(c0.x, c1.x, c2.x), fbits_low_bytes(c0.y, c1.y, c2.y),
+                          fbits_low_bytes(c0.z, c1.z, c2.z), fbits_low_bytes(c0.w, c1.w, c2.w)};
+#if GSWM_EMIT_PAIRS
+  // two float4 per call: bucket bits of elements 4i..4i+3 are byte i>>1 of the tile's (keystream ^ message), high nibble first
+  auto emit2 = [&](uint32_t ia, uint32_t ib, const uint32_t (&fa)[4], const uint32_t (&fb)[4]) {
+    if (kGuard && ia >= n_f4) return;
+    const float4 sa = my_sign[2u * s_bytes[ia >> 1]];
+    const float4 sb = my_sign[2u * s_bytes[(kGuard && ib >= n_f4 ? ia : ib) >> 1]];
+    float4 za, zb;
+    bucket_quantile8_f32(fa, fb, sa, sb, za, zb);
+    __stcs(out4 + ia, za);                                            // streaming store: written once, never re-read
+    if (!kGuard || ib < n_f4) __stcs(out4 + ib, zb);
+  };
+  emit2(i0, i0 + kThreads, f0, f1);
+  emit2(i0 + 2 * kThreads, i0 + 3 * kThreads, f2, f3);
+#else
+  auto emit = [&](uint32_t i, const uint32_t (&f)[4]) {
+    if (kGuard && i >= n_f4) return;
+    const float4 sgn = my_sign[2u * s_bytes[i >> 1]];
+    __stcs(out4 + i, bucket_quantile4_f32(f[0], f[1], f[2], f[3], sgn));
+  };
+  emit(i0, f0);
+  emit(i0 + kThreads, f1);
+  emit(i0 + 2 * kThreads, f2);
+  emit(i0 + 3 * kThreads, f3);
+#endif
+}
+
+// Grid (X, Y).  CTA (x, y) owns one fixed piece of the latent layout -- so its 2 KB of (keystream ^ message), its
+// sign LUT and its Philox offset are set up ONCE -- and walks the latents x, x + X, x + 2X, ...
+//   shared key : Y = non-empty HALF tiles of a latent; CTA (x, h) produces super-iterations {2(h&1), 2(h&1)+1} of tile
+//                h>>1 (two independent instruction streams).  X * Y is sized to the CTAs the GPU holds at once
+//                (persistent); nothing in the latent loop synchronises, warps drift freely.  CTA (0, 2t) computes slice
+//                t of the shared table, every CTA of tile t acquires it (the producer has the lowest linear index of its
+//                consumers, so it is dispatched no later than any of them and never waits itself).
+//   per-latent : Y = tiles, X = n_latents (one latent per CTA): warp 0 computes the tile's keystream between two barriers
+//                while the SM's other CTAs keep its issue slots busy.
+// Resident CTAs per SM.  Shared key: 4 (64 registers: two super-iterations in flight without spills; measured 69.7 us per
+// 4096 SD-2.1 latents against 73.6 at 6 x 40 registers).  Per-latent keys: 6, one latent per CTA -- while warp 0 computes a
+// tile's ChaCha20 blocks the other CTAs of the SM keep its issue slots busy, so more and smaller CTAs win there.
+#ifndef GSWM_EMBED_MINB
+#define GSWM_EMBED_MINB 4
+#endif
+#ifndef GSWM_EMBED_MINB_PER_LATENT
+#define GSWM_EMBED_MINB_PER_LATENT 6
+#endif
 template <bool kPerLatent>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, kPerLatent ? GSWM_EMBED_MINB_PER_LATENT : GSWM_EMBED_MINB)
 embed_kernel(const EmbedArgs a) {
   __shared__ __align__(16) uint32_t s_ks[kTileWords];
   __shared__ __align__(16) float4 s_sign[512];
-  const int64_t latent = blockIdx.x;
-  const uint32_t tile = blockIdx.y;
-  const int64_t tile_base = (int64_t)tile * kTileElems;
+  const uint32_t tile = kPerLatent ? blockIdx.y : blockIdx.y >> 1;
+  const uint32_t tiles = a.tiles_per_latent;
   const uint32_t words = tile_words(a.n_elems, tile);
   const uint32_t n_f4 = tile_elems(a.n_elems, tile) >> 2;
   build_sign_lut(s_sign);
-  embed_stage<kPerLatent>(s_ks, a, latent, tile, words);             // ends with __syncthreads()
-
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
-  float4* out4 = reinterpret_cast<float4*>(a.out + latent * a.n_elems + tile_base);
-  // Philox counter of this thread's super-iteration s: G = ((global_latent * tiles + tile) * 4 + s) * 256 + tid
-  const uint64_t g_tile = ((uint64_t)(a.first_latent + latent) * gridDim.y + tile) * (4ull * kThreads) + threadIdx.x;
   const float4* my_sign = s_sign + (threadIdx.x & 1u);               // i & 1 == threadIdx.x & 1 for every float4
+  const uint64_t tile_stride = 4ull * kThreads;                       // Philox counters per tile
+  const uint64_t n_f4_latent = (uint64_t)(a.n_elems >> 2);
+  float4* out4 = reinterpret_cast<float4*>(a.out) + (blockIdx.x * n_f4_latent + (uint64_t)tile * kTileF4);
+  uint64_t g_tile = ((uint64_t)(a.first_latent + blockIdx.x) * tiles + tile) * tile_stride + threadIdx.x;
+  const uint64_t out_step = gridDim.x * n_f4_latent;
+  const uint64_t g_step = (uint64_t)gridDim.x * tiles * tile_stride;
 
-  auto emit = [&](uint32_t i, uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, bool guard) {
-    if (guard && i >= n_f4) return;
-    // bucket bits of elements 4i..4i+3: byte i>>1 of the tile's (keystream ^ message), high nibble first
-    const float4 sgn = my_sign[2u * s_bytes[i >> 1]];
-    out4[i] = bucket_quantile4_f32(f0, f1, f2, f3, sgn);
-  };
-  auto super_iteration = [&](uint32_t sidx, bool guard) {
-    const uint64_t g = g_tile + (uint64_t)sidx * kThreads;
-    const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
-    const uint4 c0 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 0u), a.seed_lo, a.seed_hi);
-    const uint4 c1 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 1u), a.seed_lo, a.seed_hi);
-    const uint4 c2 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 2u), a.seed_lo, a.seed_hi);
-    const uint32_t i0 = (4u * sidx) * kThreads + threadIdx.x;
-    emit(i0, fbits_top23(c0.x), fbits_top23(c0.y), fbits_top23(c0.z), fbits_top23(c0.w), guard);
-    emit(i0 + kThreads, fbits_top23(c1.x), fbits_top23(c1.y), fbits_top23(c1.z), fbits_top23(c1.w), guard);
-    emit(i0 + 2 * kThreads, fbits_top23(c2.x), fbits_top23(c2.y), fbits_top23(c2.z), fbits_top23(c2.w), guard);
-    emit(i0 + 3 * kThreads, fbits_low_bytes(c0.x, c1.x, c2.x), fbits_low_bytes(c0.y, c1.y, c2.y),
-         fbits_low_bytes(c0.z, c1.z, c2.z), fbits_low_bytes(c0.w, c1.w, c2.w), guard);
-  };
-  if (n_f4 == kTileF4) {                       // full tile: constant trip count, no bounds checks
-#pragma unroll 2
-    for (uint32_t sidx = 0; sidx < 4; ++sidx) super_iteration(sidx, false);
+  if constexpr (!kPerLatent) {
+    if (blockIdx.x == 0 && (blockIdx.y & 1u) == 0 && threadIdx.x < 32)
+      publish_shared_slice(a.tab, a.keys, a.nonces, a.msgs, a.n_elems, tile, a.msg_words, a.tiled_words);
+    acquire_shared_slice(s_ks, a.tab, tile, words);                   // ends with __syncthreads(): LUT + keystream visible
+    const uint32_t s0 = (blockIdx.y & 1u) * 2u;                       // the launch only creates non-empty halves
+    if (n_f4 == kTileF4) {
+      for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
+        embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4);
+        embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4);
+      }
+    } else {
+      for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
+        embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4);
+        if ((s0 + 1) * 4 * kThreads < n_f4) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4);
+      }
+    }
   } else {
-    for (uint32_t sidx = 0; sidx * 4 * kThreads < n_f4; ++sidx) super_iteration(sidx, true);
+    for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
+      __syncthreads();                                                // previous latent's readers are done with s_ks (first pass: LUT built)
+      compute_private_slice(s_ks, a.keys, a.nonces, a.msgs + latent * (int64_t)a.msg_stride_bytes, latent, tile, words,
+                            a.msg_words, a.tiled_words);
+      if (n_f4 == kTileF4) {
+#pragma unroll 2
+        for (uint32_t sidx = 0; sidx < 4; ++sidx) embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4);
+      } else {
+        for (uint32_t sidx = 0; sidx * 4 * kThreads < n_f4; ++sidx) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4);
+      }
+    }
   }
 }
 
@@ -439,10 +529,8 @@ extract_kernel(const ExtractArgs a) {
   if (threadIdx.x == 0) {
     for (int64_t q = 0; q < kStages - 1; ++q) issue(q);               // kStages-1 chunks in flight from the start
   }
-  if constexpr (!kPerLatent) {                  // the first CTAs each produce slices of the shared keystream
-    for (uint32_t t = blockIdx.x; t < a.tiles_per_latent; t += gridDim.x)
-      publish_shared_slice(a.tab, a.keys, a.nonces, nullptr, a.n_elems, t, 0, 0);
-  }
+  if constexpr (!kPerLatent)                    // CTA 0 produces the shared keystream table for the whole grid
+    produce_shared_table(a.tab, a.keys, a.nonces, nullptr, a.n_elems, a.tiles_per_latent, 0, 0);
 
   if constexpr (!kPerLatent) {                  // a latent's whole keystream fits the cache: stage it once per CTA
     for (uint32_t t = 0; t < a.ks_cache_tiles; ++t)
@@ -597,7 +685,7 @@ static int check_job(const gswm_job* job, bool for_extract) {
   if (for_extract && (job->n_elems % job->msg_bits) != 0) return GSWM_E_MSGLEN;
   if (job->n_elems > ((int64_t)1 << 31)) return GSWM_E_RANGE;
   const int64_t tiles = (job->n_elems + kTileElems - 1) / kTileElems;
-  if (job->n_latents > 0x7FFFFFFFll || tiles > 65535) return GSWM_E_RANGE;
+  if (job->n_latents > 0x7FFFFFFFll || tiles > 32767) return GSWM_E_RANGE;    // grid.y carries tiles or half tiles
   return GSWM_OK;
 }
 
@@ -640,14 +728,17 @@ static EmbedArgs make_embed_args(const gswm_job* job) {
   a.nonces = job->d_nonces;
   a.msgs = job->d_msgs;
   a.n_elems = job->n_elems;
+  a.n_latents = job->n_latents;
+  a.tiles_per_latent = tiles_of(job->n_elems);
   a.msg_words = (uint32_t)job->msg_bits / 32;
   a.tiled_words = (uint32_t)(job->n_elems / job->msg_bits) * a.msg_words;
   a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
   return a;
 }
 
-template <typename K>
-static int launch_extract_kernel(K kernel, const ExtractArgs& a, size_t smem, cudaStream_t st) {
+// Persistent launch: grid = min(work items, SMs x resident CTAs of this kernel at this shared-memory size).
+template <typename K, typename Args>
+static int launch_persistent(K kernel, const Args& a, int64_t items, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int dev = 0, sms = 0, per_sm = 0;
@@ -656,9 +747,30 @@ static int launch_extract_kernel(K kernel, const ExtractArgs& a, size_t smem, cu
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem)) != cudaSuccess) return (int)e;
   if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
   const int64_t resident = (int64_t)sms * per_sm;
-  const unsigned grid = (unsigned)(a.n_latents < resident ? a.n_latents : resident);
+  const unsigned grid = (unsigned)(items < resident ? items : resident);
   kernel<<<grid, kThreads, smem, st>>>(a);
   return (int)cudaGetLastError();
+}
+
+// Embed grid (X, Y): Y fixed pieces of a latent (half tiles / tiles), X latent lanes.  Persistent: X * Y CTAs fill the GPU once.
+template <typename K>
+static int launch_embed(K kernel, const EmbedArgs& a, unsigned y, bool persistent, cudaStream_t st) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0)) != cudaSuccess) return (int)e;
+  if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+  int64_t x = persistent ? ((int64_t)sms * per_sm) / y : a.n_latents;
+  if (x < 1) x = 1;
+  if (x > a.n_latents) x = a.n_latents;
+  kernel<<<dim3((unsigned)x, y), kThreads, 0, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <typename K>
+static int launch_extract_kernel(K kernel, const ExtractArgs& a, size_t smem, cudaStream_t st) {
+  return launch_persistent(kernel, a, a.n_latents, smem, st);
 }
 
 template <typename T>
@@ -753,11 +865,15 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
   a.first_latent = first_latent;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.off_lo = (uint32_t)offset; a.off_hi = (uint32_t)(offset >> 32) << 2;
-  const dim3 grid((unsigned)job->n_latents, tiles_of(job->n_elems));
-  if (job->per_latent) embed_kernel<true><<<grid, kThreads, 0, st>>>(a);
-  else embed_kernel<false><<<grid, kThreads, 0, st>>>(a);
+  for (int r = 0; r < GSWM_PHILOX_ROUNDS; ++r) {
+    a.rk.k[2 * r] = a.seed_lo + (uint32_t)r * 0x9E3779B9u;
+    a.rk.k[2 * r + 1] = a.seed_hi + (uint32_t)r * 0xBB67AE85u;
+  }
+  const unsigned halves = (unsigned)((job->n_elems / 4 + 8 * kThreads - 1) / (8 * kThreads));   // non-empty half tiles
+  rc = job->per_latent ? launch_embed(embed_kernel<true>, a, a.tiles_per_latent, false, st)
+                       : launch_embed(embed_kernel<false>, a, halves, true, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
+  return rc;
 }
 
 int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_latent, void* d_out,

@@ -72,6 +72,27 @@ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 
+// Same generator with the round keys (k0 + r W0, k1 + r W1) precomputed by the host into kernel-parameter space:
+// the xor then takes its key straight from the constant bank instead of from a uniform register that has to be
+// rematerialised with a UIADD3 per key per loop iteration.
+struct PhiloxKeys {
+  uint32_t k[2 * GSWM_PHILOX_ROUNDS];
+};
+__device__ __forceinline__ uint4 philox4x32_keys(uint4 c, const PhiloxKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < GSWM_PHILOX_ROUNDS; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
+    uint4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ rk.k[2 * r];
+    n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ rk.k[2 * r + 1];
+    n.w = (uint32_t)p0;
+    c = n;
+  }
+  return c;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The product's uniform source ("gswm uniforms v2", restated in oracle/gs_oracle.py:gswm_uniform_grid).
 //
@@ -219,6 +240,45 @@ __device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1,
   return make_float4(g01.x, g01.y, g23.x, g23.y);
 #endif
 #endif
+}
+
+// Eight elements (two float4) at once: four independent packed Horner chains in one basic block, and ONE
+// compare-and-branch for the rare tail patch -- the branch is a scheduling barrier, so halving their number both
+// saves issue slots and lets the four chains hide each other's FFMA latency.
+__device__ __forceinline__ void bucket_quantile8_f32(const uint32_t (&fa)[4], const uint32_t (&fb)[4], float4 sa, float4 sb,
+                                                     float4& za, float4& zb) {
+  float2 v0, v1, v2, v3, x0, x1, x2, x3;
+  quantile_front2(fa[0], fa[1], v0, x0);
+  quantile_front2(fa[2], fa[3], v1, x1);
+  quantile_front2(fb[0], fb[1], v2, x2);
+  quantile_front2(fb[2], fb[3], v3, x3);
+  const float c[] = {GSWM_HNQ_CENTRAL_COEFFS};
+  float2 p0 = splat2(c[0]), p1 = p0, p2 = p0, p3 = p0;
+#pragma unroll
+  for (int i = 1; i < (int)(sizeof(c) / sizeof(float)); ++i) {
+    p0 = __ffma2_rn(p0, x0, splat2(c[i]));
+    p1 = __ffma2_rn(p1, x1, splat2(c[i]));
+    p2 = __ffma2_rn(p2, x2, splat2(c[i]));
+    p3 = __ffma2_rn(p3, x3, splat2(c[i]));
+  }
+  float2 g0 = __fmul2_rn(v0, p0), g1 = __fmul2_rn(v1, p1), g2 = __fmul2_rn(v2, p2), g3 = __fmul2_rn(v3, p3);
+  const float lo = fminf(fminf(fminf(x0.x, x0.y), fminf(x1.x, x1.y)), fminf(fminf(x2.x, x2.y), fminf(x3.x, x3.y)));
+  if (lo < GSWM_HNQ_XSPLIT) {
+    if (x0.x < GSWM_HNQ_XSPLIT) g0.x = quantile_tail(x0.x);
+    if (x0.y < GSWM_HNQ_XSPLIT) g0.y = quantile_tail(x0.y);
+    if (x1.x < GSWM_HNQ_XSPLIT) g1.x = quantile_tail(x1.x);
+    if (x1.y < GSWM_HNQ_XSPLIT) g1.y = quantile_tail(x1.y);
+    if (x2.x < GSWM_HNQ_XSPLIT) g2.x = quantile_tail(x2.x);
+    if (x2.y < GSWM_HNQ_XSPLIT) g2.y = quantile_tail(x2.y);
+    if (x3.x < GSWM_HNQ_XSPLIT) g3.x = quantile_tail(x3.x);
+    if (x3.y < GSWM_HNQ_XSPLIT) g3.y = quantile_tail(x3.y);
+  }
+  g0 = __fmul2_rn(g0, make_float2(sa.x, sa.y));
+  g1 = __fmul2_rn(g1, make_float2(sa.z, sa.w));
+  g2 = __fmul2_rn(g2, make_float2(sb.x, sb.y));
+  g3 = __fmul2_rn(g3, make_float2(sb.z, sb.w));
+  za = make_float4(g0.x, g0.y, g1.x, g1.y);
+  zb = make_float4(g2.x, g2.y, g3.x, g3.y);
 }
 
 // ------------------------------------------------------------------------------------------------

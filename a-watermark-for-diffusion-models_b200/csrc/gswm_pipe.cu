@@ -7,9 +7,13 @@
 // Each slot owns one stream; everything for a chunk is enqueued in order on its slot's stream, so device
 // buffer reuse two chunks later is ordered by the stream itself.  Nothing in the chunk loop blocks the
 // host: key material is uploaded once per call through a pinned staging buffer, and the small per-chunk
-// outputs (messages, counts, matched) land in per-slot pinned staging that is copied to the caller's
-// (possibly pageable) arrays when the slot comes round again.  The big latent buffers are copied
-// straight from / to the caller's memory: pinned memory there gives the full PCIe rate.
+// outputs (messages, counts, matched) are WRITTEN BY THE EXTRACT KERNEL ITSELF into per-slot pinned host
+// staging (mapped memory, posted PCIe writes) and handed to the caller's (possibly pageable) arrays when
+// the slot comes round again.  They must not go through the copy engine: a 32-byte D2H copy queues behind
+// whatever 16 MB D2H copy another pipe (the embed side) has in flight on the same engine, and the slot's
+// next H2D cannot start until it is through -- measured 7.0 ms instead of 5.4 ms per 4096-latent pair with
+// both directions busy (tools/e2ebench.py).  The big latent buffers are copied straight from / to the
+// caller's memory: pinned memory there gives the full PCIe rate.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -26,16 +30,14 @@ constexpr int kMaxMsgBytes = 1024;   // msg_bits <= 8192
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;  // recorded after the chunk's last D2H
+  cudaEvent_t done = nullptr;  // recorded after the chunk's kernel (its outputs are then visible in the staging)
   void* d_in = nullptr;        // z (extract) or u (injected embed): chunk * max_elems * 8 bytes
   void* d_out = nullptr;       // latents out (embed): chunk * max_elems * 8 bytes
   void* d_ws = nullptr;        // gswm_workspace_bytes for max_elems
-  uint8_t* d_msg_out = nullptr;   // chunk * kMaxMsgBytes
-  uint16_t* d_counts = nullptr;   // chunk * 8192
-  int32_t* d_matched = nullptr;   // chunk
-  uint8_t* h_msg_out = nullptr;   // pinned staging of the three outputs above
-  uint16_t* h_counts = nullptr;
-  int32_t* h_matched = nullptr;
+  // pinned, device-visible host staging the extract kernel writes its small outputs into
+  uint8_t* h_msg_out = nullptr;   // chunk * kMaxMsgBytes
+  uint16_t* h_counts = nullptr;   // chunk * 8192
+  int32_t* h_matched = nullptr;   // chunk
   // what the staging currently holds (to be delivered to the caller), -1 = nothing
   int64_t pending_first = -1, pending_n = 0;
 };
@@ -48,6 +50,7 @@ struct gswm_pipe {
   int64_t chunk = 0;
   Slot slot[kSlots];
   int64_t* d_counters = nullptr;
+  int64_t* h_counters = nullptr;   // mapped host copy, written by publish_counters_kernel
   // key material of the current call, uploaded once: [keys | nonces | msgs], grown on demand
   uint8_t* d_km = nullptr;
   uint8_t* h_km = nullptr;      // pinned staging
@@ -61,6 +64,12 @@ namespace {
     cudaError_t e_ = (expr);                 \
     if (e_ != cudaSuccess) return (int)e_;   \
   } while (0)
+
+// The call's counters go back to the host the same way as the per-latent outputs: a one-warp kernel stores them into
+// mapped host memory, so the result never waits in a copy-engine queue.
+__global__ void publish_counters_kernel(const int64_t* __restrict__ d, int64_t* __restrict__ h) {
+  if (threadIdx.x < GSWM_N_COUNTERS) h[threadIdx.x] = d[threadIdx.x];
+}
 
 int check_host_job(const gswm_pipe* p, const gswm_host_job* j, bool need_msg) {
   if (!p || !j || !j->h_keys || !j->h_nonces) return GSWM_E_NULL;
@@ -163,8 +172,8 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
   auto A = [&](void** ptr, size_t bytes) {
     if (rc == 0) rc = (int)cudaMalloc(ptr, bytes);
   };
-  auto H = [&](void** ptr, size_t bytes) {
-    if (rc == 0) rc = (int)cudaMallocHost(ptr, bytes);
+  auto H = [&](void** ptr, size_t bytes) {   // pinned + mapped: under unified addressing the kernel uses the same pointer
+    if (rc == 0) rc = (int)cudaHostAlloc(ptr, bytes, cudaHostAllocMapped);
   };
   for (auto& s : p->slot) {
     if (rc == 0) rc = (int)cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
@@ -172,14 +181,12 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
     A(&s.d_in, lat_bytes);
     A(&s.d_out, lat_bytes);
     A(&s.d_ws, ws_bytes);
-    A((void**)&s.d_msg_out, (size_t)p->chunk * kMaxMsgBytes);
-    A((void**)&s.d_counts, (size_t)p->chunk * 8192 * sizeof(uint16_t));
-    A((void**)&s.d_matched, (size_t)p->chunk * sizeof(int32_t));
     H((void**)&s.h_msg_out, (size_t)p->chunk * kMaxMsgBytes);
     H((void**)&s.h_counts, (size_t)p->chunk * 8192 * sizeof(uint16_t));
     H((void**)&s.h_matched, (size_t)p->chunk * sizeof(int32_t));
   }
   A((void**)&p->d_counters, GSWM_N_COUNTERS * sizeof(int64_t));
+  H((void**)&p->h_counters, GSWM_N_COUNTERS * sizeof(int64_t));
   if (rc != 0) {
     gswm_pipe_destroy(p);
     return rc;
@@ -193,12 +200,13 @@ void gswm_pipe_destroy(gswm_pipe* p) {
   cudaSetDevice(p->device);
   for (auto& s : p->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_ws); cudaFree(s.d_msg_out); cudaFree(s.d_counts); cudaFree(s.d_matched);
+    cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_ws);
     cudaFreeHost(s.h_msg_out); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_matched);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   cudaFree(p->d_counters);
+  cudaFreeHost(p->h_counters);
   cudaFree(p->d_km);
   cudaFreeHost(p->h_km);
   delete p;
@@ -281,13 +289,9 @@ int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, i
     chunk_job(job, dk, first, n, &dj);
     if ((rc = (int)cudaMemcpyAsync(s.d_in, reinterpret_cast<const char*>(h_z) + (size_t)first * z_row, (size_t)n * z_row,
                                    cudaMemcpyHostToDevice, s.stream))) break;
-    if ((rc = gswm_extract(&dj, s.d_in, z_dtype, s.d_msg_out, h_counts ? s.d_counts : nullptr,
-                           want_matched ? s.d_matched : nullptr, p->d_counters, s.d_ws, s.stream))) break;
-    if ((rc = (int)cudaMemcpyAsync(s.h_msg_out, s.d_msg_out, (size_t)(n * mb), cudaMemcpyDeviceToHost, s.stream))) break;
-    if (h_counts && (rc = (int)cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)(n * job->msg_bits) * sizeof(uint16_t),
-                                               cudaMemcpyDeviceToHost, s.stream))) break;
-    if (want_matched && (rc = (int)cudaMemcpyAsync(s.h_matched, s.d_matched, (size_t)n * sizeof(int32_t),
-                                                   cudaMemcpyDeviceToHost, s.stream))) break;
+    // small outputs: the kernel stores them straight into the slot's mapped host staging (no copy-engine work)
+    if ((rc = gswm_extract(&dj, s.d_in, z_dtype, s.h_msg_out, h_counts ? s.h_counts : nullptr,
+                           want_matched ? s.h_matched : nullptr, p->d_counters, s.d_ws, s.stream))) break;
     if ((rc = (int)cudaEventRecord(s.done, s.stream))) break;
     s.pending_first = first;
     s.pending_n = n;
@@ -296,9 +300,18 @@ int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, i
     const int r2 = drain_slot(s, mb, job->msg_bits, h_msg_out, h_counts, want_matched ? h_matched : nullptr);
     if (rc == 0) rc = r2;
   }
+  if (rc == 0 && h_counters) {               // after every slot's kernels: slot 0 waits for the others, then publishes
+    for (int k = 1; k < kSlots && rc == 0; ++k) {
+      rc = (int)cudaEventRecord(p->slot[k].done, p->slot[k].stream);
+      if (rc == 0) rc = (int)cudaStreamWaitEvent(p->slot[0].stream, p->slot[k].done, 0);
+    }
+    if (rc == 0) {
+      publish_counters_kernel<<<1, 32, 0, p->slot[0].stream>>>(p->d_counters, p->h_counters);
+      rc = (int)cudaGetLastError();
+    }
+  }
   rc = sync_all(p, rc);
-  if (rc == 0 && h_counters)
-    rc = (int)cudaMemcpy(h_counters, p->d_counters, GSWM_N_COUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost);
+  if (rc == 0 && h_counters) std::memcpy(h_counters, p->h_counters, GSWM_N_COUNTERS * sizeof(int64_t));
   return rc;
 }
 

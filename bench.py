@@ -33,6 +33,7 @@ UNIT = "latents/s"
 SHAPES = {"sd21": (4, 64, 64), "sdxl": (4, 128, 128)}
 SIGMA = 0.325
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+E2E_CHUNK = 1024              # latents per pipe chunk: each copy-engine switch costs ~65 us with both PCIe directions busy (tools/e2ebench.py)
 
 
 def parse():
@@ -331,8 +332,8 @@ def run_gpu_arm(args):
     # Two pipes (one per direction) driven from two host threads: the embed side's D2H and the extract side's H2D
     # use the two directions of the PCIe link at the same time (ctypes releases the GIL during the calls).
     import threading
-    pipe_e = gswm.HostPipe(local, max_elems=n, chunk_latents=256)
-    pipe_x = gswm.HostPipe(local, max_elems=n, chunk_latents=256)
+    pipe_e = gswm.HostPipe(local, max_elems=n, chunk_latents=E2E_CHUNK)
+    pipe_x = gswm.HostPipe(local, max_elems=n, chunk_latents=E2E_CHUNK)
     h_out = torch.empty((B, *shape), dtype=torch.float32).pin_memory()
     h_in = z_noisy.cpu().pin_memory()
     e2e_steps = max(1, args.e2e_steps)
@@ -404,7 +405,7 @@ def run_gpu_arm(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "decode_exact": bool(e2e_ok),
-                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), 256-latent chunks, 2 slots each"},
+                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), %d-latent chunks, 2 slots each" % E2E_CHUNK},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
