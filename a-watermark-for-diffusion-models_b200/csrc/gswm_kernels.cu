@@ -31,8 +31,8 @@ constexpr int kTileF4 = kTileElems / 4;      // 4096 float4 per tile
 static std::atomic<int64_t> g_launches{0};
 
 // Reference extract.py:83: int(norm.cdf(z) * 2) == 1  <=>  z >= -6.957291061679417e-17 (float64).
-// Smallest fp32 that is >= that double; for fp16/bf16 inputs the comparison is simply z >= 0
-// because no half/bfloat16 value lies in [-6.96e-17, 0) other than -0.0 (which is >= the threshold).
+// Smallest fp32 that is >= that double (0xA4A06C98); bf16 inputs use its truncation 0xA4A0, fp16 inputs +0 (no fp16
+// value other than -0.0 lies in [-6.96e-17, 0)) -- see NegatedBits16.
 __device__ __forceinline__ float quantise_threshold() { return __uint_as_float(0xA4A06C98u); }
 
 __device__ __forceinline__ void load_key_nonce(const uint8_t* __restrict__ keys, const uint8_t* __restrict__ nonces,
@@ -378,7 +378,7 @@ embed_injected_kernel(const EmbedArgs a, const double* __restrict__ u, int u_per
 //   score  <- popc(~(msg ^ reference))                                   (extract.py:103-109)
 //
 // The latents are streamed HBM -> shared memory by the TMA engine (cp.async.bulk, 1-D, completion on
-// an mbarrier) in CHUNKS of 4096 elements through a kStages-deep ring, issued by one thread kStages-1
+// an mbarrier) in CHUNKS of 32 KB (8192 fp32 / 16384 fp16 elements) through a kStages-deep ring, issued by one thread kStages-1
 // chunks ahead of the consumers -- across latent boundaries, so the memory system never drains while a
 // latent's vote is being finalised.  The 256 threads read their four 4-element groups of the chunk with
 // conflict-free 128-bit shared loads.
@@ -406,19 +406,25 @@ struct ExtractArgs {
   uint32_t ks_cache_tiles;    // shared-key mode: tiles of keystream kept resident in shared memory (0 = restage per tile)
 };
 
-#ifndef GSWM_CHUNK
-#define GSWM_CHUNK 8192
+#ifndef GSWM_CHUNK_BYTES
+#define GSWM_CHUNK_BYTES 32768
 #endif
 #ifndef GSWM_EXTRACT_MINB
 #define GSWM_EXTRACT_MINB 3
 #endif
-constexpr int kChunkElems = GSWM_CHUNK;              // 4 (or 8) chunks per tile
-constexpr int kChunksPerTile = kTileElems / kChunkElems;
+// A chunk is a fixed number of BYTES (what the memory system has in flight per CTA is what matters): 8192 fp32 or
+// 16384 fp16 / bf16 elements -- half a tile or a whole tile.
+constexpr int kStageBytes = GSWM_CHUNK_BYTES;
+template <typename T>
+struct Chunk {
+  static constexpr int kElems = kStageBytes / (int)sizeof(T);
+  static constexpr int kPerTile = kTileElems / kElems;
+  static_assert(kPerTile >= 1 && kPerTile * kElems == kTileElems, "a chunk must divide a tile");
+};
 #ifndef GSWM_STAGES
 #define GSWM_STAGES 2
 #endif
 constexpr int kStages = GSWM_STAGES;
-constexpr int kStageBytes = kChunkElems * 4;         // sized for fp32; fp16 / bf16 use half of it
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -466,26 +472,36 @@ struct NegatedBits<float> {
   }
 };
 
-// fp16 / bf16: no value of either type lies in [T, 0) except -0.0, so "z < T" is "sign set and magnitude non-zero".
-// Both types keep the sign in bit 15 and the magnitude in bits 14..0: (m + 0x7FFF) carries into bit 15 exactly when
-// the magnitude m is non-zero (no carry crosses the 16-bit lanes because m <= 0x7FFF).  One byte permute then puts
-// bit 15 / bit 31 of the two words onto bit 7 of bytes 0..3.
+// fp16 / bf16: one packed compare (HSET2.LT) per two elements yields an all-ones halfword where z < T16, and one byte
+// permute puts the four halfwords' high bytes in place.  T16 is the smallest value of the type that is >= T:
+//   fp16 : nothing lies in [T, 0) except -0.0 (the smallest subnormal is 6e-8), so T16 = +0 -- and -0.0 < 0 is false, as
+//          the reference needs (norm.cdf(-0.0) * 2 == 1);
+//   bf16 : has fp32's exponent range, so tiny negatives in [T, 0) exist and must decode as 1: T16 = 0xA4A0
+//          (-6.94e-17, the fp32 threshold's bit pattern truncated towards zero).  Subnormals are compared, not flushed.
+template <typename T2, uint32_t kThresholdBits>
 struct NegatedBits16 {
   static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g) {
     const uint2 r = reinterpret_cast<const uint2*>(stage)[g];
-    const uint32_t nx = ((r.x & 0x7FFF7FFFu) + 0x7FFF7FFFu) & r.x;   // bit 15 / 31: element is < 0 (and not -0.0)
-    const uint32_t ny = ((r.y & 0x7FFF7FFFu) + 0x7FFF7FFFu) & r.y;
+    const uint32_t tb = kThresholdBits | (kThresholdBits << 16);
+    T2 zx, zy, thr;
+    memcpy(&zx, &r.x, 4);
+    memcpy(&zy, &r.y, 4);
+    memcpy(&thr, &tb, 4);
+    const uint32_t nx = __hlt2_mask(zx, thr);                         // 0xFFFF per halfword where z < T16
+    const uint32_t ny = __hlt2_mask(zy, thr);
     return __byte_perm(nx, ny, 0x7531);                              // bytes: x.b1, x.b3, y.b1, y.b3
   }
 };
 template <>
-struct NegatedBits<__half> : NegatedBits16 {};
+struct NegatedBits<__half> : NegatedBits16<__half2, 0x0000u> {};
 template <>
-struct NegatedBits<__nv_bfloat16> : NegatedBits16 {};
+struct NegatedBits<__nv_bfloat16> : NegatedBits16<__nv_bfloat162, 0xA4A0u> {};
 
 template <typename T, bool kPerLatent, bool kPow2>
 __global__ void __launch_bounds__(kThreads, GSWM_EXTRACT_MINB)
 extract_kernel(const ExtractArgs a) {
+  constexpr int kChunkElems = Chunk<T>::kElems;
+  constexpr int kChunksPerTile = Chunk<T>::kPerTile;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* s_stage = smem_raw;                                              // kStages x kStageBytes
   uint32_t* s_ks_all = reinterpret_cast<uint32_t*>(smem_raw + kStages * kStageBytes);  // max(1, ks_cache_tiles) x kTileWords
@@ -590,8 +606,9 @@ extract_kernel(const ExtractArgs a) {
         for (uint32_t k = 0; k * kThreads + threadIdx.x < n_grp; ++k) consume(k);
       }
       if constexpr (kPow2) {
-        adds_since_spill += kChunkElems / 4 / kThreads;                // adds per chunk
-        if (adds_since_spill > 250) {                                  // byte lanes would overflow
+        constexpr uint32_t kAddsPerChunk = kChunkElems / 4 / kThreads;
+        adds_since_spill += kAddsPerChunk;
+        if (adds_since_spill + kAddsPerChunk > 255u) {                 // the next chunk could overflow a byte lane
           c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
           packed = 0; adds_since_spill = 0;
         }
@@ -922,7 +939,8 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
   a.copies = (uint32_t)copies;
   a.n_latents = job->n_latents;
-  a.chunks_per_latent = (uint32_t)((job->n_elems + kChunkElems - 1) / kChunkElems);
+  const int64_t chunk_elems = z_dtype == GSWM_F32 ? Chunk<float>::kElems : Chunk<__half>::kElems;
+  a.chunks_per_latent = (uint32_t)((job->n_elems + chunk_elems - 1) / chunk_elems);
   const bool pow2 = (1024 % job->msg_bits) == 0;
   a.ks_cache_tiles = (!job->per_latent && a.tiles_per_latent <= 8) ? a.tiles_per_latent : 0;
   const size_t smem = (size_t)kStages * kStageBytes +

@@ -272,9 +272,30 @@ def test_extract_quantiser_edges(gswm, cuda_device, golden):
     assert np.array_equal(res.counts[0].cpu().numpy().astype(np.uint32), O.vote_counts(z, KEY, NONCE, 512))
     for dt in (torch.float16, torch.bfloat16):
         zz = torch.tensor([0.0, -0.0, 6e-8, -6e-8, 1.0, -1.0, 8.0, -65504.0] * 64, dtype=dt)
+        # bit patterns the arithmetic cannot produce by rounding: smallest / largest subnormals of either sign
+        # (bf16 has fp32's range: 0xA4A0 = -6.94e-17 is the last value that still decodes as 1, 0xA4A1 the first 0)
+        raw = torch.tensor([0x0001, 0x8001, 0x03FF, 0x83FF, 0x007F, 0x807F, 0x0080, 0x8080, 0xFBFF, 0xA4A0, 0xA4A1,
+                            0xA49F, 0xA500, 0x2420], dtype=torch.int32)
+        zz[8:8 + raw.numel()] = raw.to(torch.int16).view(dt)
         res = gswm.extract_batch(zz.reshape(1, 4, 8, 16).to(cuda_device), km, want_counts=True)
         assert np.array_equal(res.counts[0].cpu().numpy().astype(np.uint32),
-                              O.vote_counts(zz.float().numpy(), KEY, NONCE, 512))
+                              O.vote_counts(zz.float().numpy(), KEY, NONCE, 512)), dt
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_extract_saturated_counts_large_latent(gswm, cuda_device, dtype):
+    """A 2048 x 2048 image's latent (4 x 256 x 256): R = 1024 copies, a thread sees 256 of them.  With a noise-free
+    all-ones message every one of them votes 1 -- the in-register byte-lane counters must not wrap."""
+    shape, L = (4, 256, 256), 256
+    n = int(np.prod(shape))
+    for msg in (b"\xff" * 32, bytes(32), np.random.RandomState(5).bytes(32)):
+        km = gswm.KeyMaterial.make(KEY, NONCE, msg, L)
+        z = gswm.embed_batch(3, shape, km, 17, 0, 0, cuda_device).to(dtype)
+        res = gswm.extract_batch(z, km, want_counts=True)
+        want = np.unpackbits(np.frombuffer(msg, np.uint8)).astype(np.uint32) * (n // L)
+        for i in range(3):
+            assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), want)
+        assert res.messages.cpu().numpy().tobytes() == msg * 3
 
 
 def test_vote_tie_decodes_zero(gswm, cuda_device):
