@@ -16,6 +16,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <random>
 
 #include "../../include/gswm.h"
@@ -34,6 +35,14 @@ static std::atomic<int64_t> g_launches{0};
 // Smallest fp32 that is >= that double (0xA4A06C98); bf16 inputs use its truncation 0xA4A0, fp16 inputs +0 (no fp16
 // value other than -0.0 lies in [-6.96e-17, 0)) -- see NegatedBits16.
 __device__ __forceinline__ float quantise_threshold() { return __uint_as_float(0xA4A06C98u); }
+
+// Programmatic dependent launch (PDL): both throughput kernels are launched with the stream-serialisation attribute
+// relaxed, tell the hardware at once that the NEXT kernel in the stream may start being scheduled as their CTAs
+// retire, and do everything that touches global memory only after griddep_wait() -- which returns when every
+// earlier kernel in the stream has completed and flushed.  What overlaps with the predecessor's tail is the launch
+// latency and the CTA prologue (sign table, barrier init, counter reset): ~2-3 us per kernel of a ~60 us step.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void load_key_nonce(const uint8_t* __restrict__ keys, const uint8_t* __restrict__ nonces,
                                                int64_t row, uint32_t (&k)[8], uint32_t (&n)[4]) {
@@ -307,7 +316,9 @@ embed_kernel(const EmbedArgs a) {
   const uint32_t tiles = a.tiles_per_latent;
   const uint32_t words = tile_words(a.n_elems, tile);
   const uint32_t n_f4 = tile_elems(a.n_elems, tile) >> 2;
+  griddep_launch_dependents();
   build_sign_lut(s_sign);
+  griddep_wait();                                                     // nothing above touches global memory
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
   const float4* my_sign = s_sign + (threadIdx.x & 1u);               // i & 1 == threadIdx.x & 1 for every float4
   const uint64_t tile_stride = 4ull * kThreads;                       // Philox counters per tile
@@ -534,6 +545,7 @@ extract_kernel(const ExtractArgs a) {
     tma_load_1d(s_stage + (size_t)(q % kStages) * kStageBytes, src, bytes, bar, policy);
   };
 
+  griddep_launch_dependents();
   if (threadIdx.x == 0) {
     for (int sidx = 0; sidx < kStages; ++sidx) mbar_init(&s_full[sidx], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -542,6 +554,7 @@ extract_kernel(const ExtractArgs a) {
   }
   for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) s_cnt[p] = 0;
   __syncthreads();
+  griddep_wait();                                                     // nothing above touches global memory
   if (threadIdx.x == 0) {
     for (int64_t q = 0; q < kStages - 1; ++q) issue(q);               // kStages-1 chunks in flight from the start
   }
@@ -753,6 +766,31 @@ static EmbedArgs make_embed_args(const gswm_job* job) {
   return a;
 }
 
+// Launch with programmatic stream serialisation allowed (see griddep_wait above); GSWM_PDL=0 in the environment
+// falls back to ordinary stream order (the device-side griddepcontrol instructions are then no-ops).
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("GSWM_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename Args>
+static int launch_pdl(void (*kernel)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& a) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 // Persistent launch: grid = min(work items, SMs x resident CTAs of this kernel at this shared-memory size).
 template <typename K, typename Args>
 static int launch_persistent(K kernel, const Args& a, int64_t items, size_t smem, cudaStream_t st) {
@@ -765,8 +803,7 @@ static int launch_persistent(K kernel, const Args& a, int64_t items, size_t smem
   if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
   const int64_t resident = (int64_t)sms * per_sm;
   const unsigned grid = (unsigned)(items < resident ? items : resident);
-  kernel<<<grid, kThreads, smem, st>>>(a);
-  return (int)cudaGetLastError();
+  return launch_pdl(kernel, dim3(grid), smem, st, a);
 }
 
 // Embed grid (X, Y): Y fixed pieces of a latent (half tiles / tiles), X latent lanes.  Persistent: X * Y CTAs fill the GPU once.
@@ -781,8 +818,7 @@ static int launch_embed(K kernel, const EmbedArgs& a, unsigned y, bool persisten
   int64_t x = persistent ? ((int64_t)sms * per_sm) / y : a.n_latents;
   if (x < 1) x = 1;
   if (x > a.n_latents) x = a.n_latents;
-  kernel<<<dim3((unsigned)x, y), kThreads, 0, st>>>(a);
-  return (int)cudaGetLastError();
+  return launch_pdl(kernel, dim3((unsigned)x, y), 0, st, a);
 }
 
 template <typename K>
