@@ -33,7 +33,9 @@ UNIT = "latents/s"
 SHAPES = {"sd21": (4, 64, 64), "sdxl": (4, 128, 128)}
 SIGMA = 0.325
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
-E2E_CHUNK = 1024              # latents per pipe chunk: each copy-engine switch costs ~65 us with both PCIe directions busy (tools/e2ebench.py)
+E2E_CHUNK = 4096              # latents per pipe chunk.  The kernels take ~0.1 ms of a ~5.5 ms PCIe-bound step, so there is nothing to
+                              # gain from overlapping them with the copies, while every extra copy costs ~65 us when both PCIe
+                              # directions are busy (tools/e2ebench.py: 7.4 / 6.5 / 6.0 / 5.65 ms at 64 / 256 / 1024 / 4096 latents)
 
 
 def parse():
@@ -96,8 +98,10 @@ def cpu_pairs_per_second(n_elems, msg_bits, pairs_per_worker, cores):
 
 
 def calibrate_cpu(n_elems, msg_bits):
-    t, _ = _cpu_worker((4, n_elems, msg_bits, 1))
-    return t / 4
+    """Seconds per pair on one core, measured after a warm-up call (the first call pays the scipy / cryptography imports)."""
+    _cpu_worker((2, n_elems, msg_bits, 1))
+    t, _ = _cpu_worker((16, n_elems, msg_bits, 1))
+    return t / 16
 
 
 def run_reference_arm(args):
@@ -332,8 +336,8 @@ def run_gpu_arm(args):
     # Two pipes (one per direction) driven from two host threads: the embed side's D2H and the extract side's H2D
     # use the two directions of the PCIe link at the same time (ctypes releases the GIL during the calls).
     import threading
-    pipe_e = gswm.HostPipe(local, max_elems=n, chunk_latents=E2E_CHUNK)
-    pipe_x = gswm.HostPipe(local, max_elems=n, chunk_latents=E2E_CHUNK)
+    pipe_e = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, B))
+    pipe_x = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, B))
     h_out = torch.empty((B, *shape), dtype=torch.float32).pin_memory()
     h_in = z_noisy.cpu().pin_memory()
     e2e_steps = max(1, args.e2e_steps)
@@ -405,7 +409,7 @@ def run_gpu_arm(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "decode_exact": bool(e2e_ok),
-                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), %d-latent chunks, 2 slots each" % E2E_CHUNK},
+                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), %d-latent chunks, 2 slots each" % min(E2E_CHUNK, B)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
