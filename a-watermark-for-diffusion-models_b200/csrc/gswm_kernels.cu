@@ -791,6 +791,14 @@ static int launch_pdl(void (*kernel)(const Args), dim3 grid, size_t smem, cudaSt
   return (int)cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
+// Tuning knob for co-scheduling experiments (tools/cobench.py): an environment variable may LOWER the number of
+// CTAs per SM a persistent grid is sized for, leaving room for another kernel on the same SMs.
+static int cap_ctas(int per_sm, const char* env_name) {
+  const char* e = std::getenv(env_name);
+  const int c = e ? std::atoi(e) : 0;
+  return (c >= 1 && c < per_sm) ? c : per_sm;
+}
+
 // Persistent launch: grid = min(work items, SMs x resident CTAs of this kernel at this shared-memory size).
 template <typename K, typename Args>
 static int launch_persistent(K kernel, const Args& a, int64_t items, size_t smem, cudaStream_t st) {
@@ -801,6 +809,7 @@ static int launch_persistent(K kernel, const Args& a, int64_t items, size_t smem
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem)) != cudaSuccess) return (int)e;
   if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+  per_sm = cap_ctas(per_sm, "GSWM_EXTRACT_CTAS_PER_SM");
   const int64_t resident = (int64_t)sms * per_sm;
   const unsigned grid = (unsigned)(items < resident ? items : resident);
   return launch_pdl(kernel, dim3(grid), smem, st, a);
@@ -815,6 +824,7 @@ static int launch_embed(K kernel, const EmbedArgs& a, unsigned y, bool persisten
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0)) != cudaSuccess) return (int)e;
   if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+  per_sm = cap_ctas(per_sm, "GSWM_EMBED_CTAS_PER_SM");
   int64_t x = persistent ? ((int64_t)sms * per_sm) / y : a.n_latents;
   if (x < 1) x = 1;
   if (x > a.n_latents) x = a.n_latents;
@@ -880,6 +890,8 @@ int gswm_debug_norm_ppf(const double* d_p, int64_t n, double* d_out, void* strea
 }
 
 int64_t gswm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gswm_philox_rounds(void) { return GSWM_PHILOX_ROUNDS; }
 
 size_t gswm_workspace_bytes(const gswm_job* job) {
   if (!job || job->per_latent || job->n_elems <= 0) return 0;

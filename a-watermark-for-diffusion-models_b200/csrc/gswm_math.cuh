@@ -1,6 +1,6 @@
 // Device-side building blocks of the Gaussian-Shading codec for sm_100a:
 //   * ChaCha20 block function, one block per thread (integer add / xor / funnel-shift rotate);
-//   * Philox4x32-10 counter-based generator (the product's uniform source);
+//   * Philox4x32 counter-based generator (the product's uniform source);
 //   * half-normal quantile g(v) = sqrt(2) erfinv(v) in fp32 (registers only: 1 MUFU.LG2 + FFMAs) and
 //     fp64 (injected-uniform mode), coefficients from tools/fit_halfnormal_quantile.py.
 // Nothing here touches memory.
@@ -48,11 +48,20 @@ __device__ __forceinline__ void chacha20_block(const uint32_t (&key)[8], const u
 }
 
 // ------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Takes the place of np.random.uniform at
+// Philox4x32-R (Salmon, Moraes, Dror, Shaw, SC'11).  Takes the place of np.random.uniform at
 // gs_insert.py:62; restated for the oracle in oracle/gs_oracle.py:philox4x32.
+//
+// R = 7 by default: Philox4x32-7 is the fewest rounds the authors report as Crush-resistant (passes TestU01
+// SmallCrush, Crush and BigCrush; Table 2 of the paper -- 10 rounds is their "with safety margin" variant).  The
+// generator it stands in for, numpy's MT19937, does not pass BigCrush (linear-complexity tests), so 7 rounds is not
+// a step down from the reference; and the secrecy of the watermark rests on the ChaCha20 keystream that picks the
+// bucket, not on the within-bucket uniform.  The embed kernel is bound by the FMA-heavy pipe that executes
+// Philox's IMAD.WIDE, so rounds are time: 58.9 us (R = 7) against 66.9 us (R = 10) per 4096 SD-2.1 latents.
+// -DGSWM_PHILOX_ROUNDS=10 builds the curand-compatible round count (oracle: GSWM_PHILOX_ROUNDS in gs_oracle.py;
+// gswm_philox_rounds() reports what a library was built with).
 // ------------------------------------------------------------------------------------------------
 #ifndef GSWM_PHILOX_ROUNDS
-#define GSWM_PHILOX_ROUNDS 10
+#define GSWM_PHILOX_ROUNDS 7
 #endif
 template <int kRounds = GSWM_PHILOX_ROUNDS>
 __device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {

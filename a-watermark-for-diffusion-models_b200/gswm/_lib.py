@@ -24,7 +24,7 @@ EXPORTS = [
     "gswm_abi_version", "gswm_strerror", "gswm_workspace_bytes", "gswm_chacha20_keystream", "gswm_embed",
     "gswm_embed_injected", "gswm_extract", "gswm_pipe_create", "gswm_pipe_destroy", "gswm_pipe_embed",
     "gswm_pipe_embed_injected", "gswm_pipe_extract", "gswm_launch_count", "gswm_debug_bucket_quantile",
-    "gswm_debug_norm_ppf",
+    "gswm_debug_norm_ppf", "gswm_philox_rounds",
 ]
 
 
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         L.gswm_pipe_embed_injected.argtypes = [vp, JP, vp, i32, vp, i32]
         L.gswm_pipe_extract.argtypes = [vp, JP, vp, i32, vp, vp, vp, vp]
         L.gswm_launch_count.restype = i64
+        L.gswm_philox_rounds.restype = C.c_int
         L.gswm_debug_bucket_quantile.argtypes = [vp, i64, i32, i32, vp, vp]
         L.gswm_debug_bucket_quantile.restype = C.c_int
         L.gswm_debug_norm_ppf.argtypes = [vp, i64, vp, vp]

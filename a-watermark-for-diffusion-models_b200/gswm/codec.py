@@ -182,7 +182,7 @@ def chacha20_keystream(keys: BytesLike, nonces: BytesLike, n_bytes: int, device=
 def embed_batch(n_latents: int, latent_shape: Sequence[int], km: KeyMaterial, seed: int, offset: int = 0,
                 first_latent: int = 0, device="cuda", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Watermarked initial noise [n_latents, *latent_shape] fp32 on ``device`` with the in-kernel
-    uniform source (Philox4x32-10 keyed by ``seed``; global latent index ``first_latent + b``)."""
+    uniform source (Philox4x32-7 keyed by ``seed``; global latent index ``first_latent + b``)."""
     dev = _device(device)
     n = _n_elems(latent_shape)
     with torch.cuda.device(dev):

@@ -257,24 +257,37 @@ def run_gpu_arm(args):
     ws2 = torch.empty_like(dj.workspace) if dj.workspace is not None else None
     ws2p = ws2.data_ptr() if ws2 is not None else None
 
-    def step(ev=None):
-        if ev:
-            ev[0].record(stream)
+    # The two halves of a step are independent (embed writes z, extract reads z_noisy), one is bound by the FMA pipes
+    # and the other by HBM, so they are launched on two streams and share the SMs: the step then runs at the pair's
+    # HBM roofline instead of the sum of two kernels each leaving one resource idle (tools/cobench.py).
+    xstream = torch.cuda.Stream(dev)
+    xp = xstream.cuda_stream
+
+    def step(serial=False):
         gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
-        if ev:
-            ev[1].record(stream)
         gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
-                                         counters.data_ptr(), ws2p, sp), "gswm_extract")
-        if ev:
-            ev[2].record(stream)
-        if world > 1:
+                                         counters.data_ptr(), ws2p, sp if serial else xp), "gswm_extract")
+        if world > 1 and not serial:
             # the only collective: 32 bytes of bit-match counters, all-reduced on a side stream so it overlaps the
-            # next step's embed (counters keep accumulating locally; `reduced` is the cross-rank total so far)
-            done.record(stream)
+            # next step (counters keep accumulating locally; `reduced` is the cross-rank total so far)
+            done.record(xstream)
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 reduced.copy_(counters)
                 dist.all_reduce(reduced)
+
+    def timed(n_steps, serial=False):
+        """Device time of n_steps steps: fork the extract stream off the launch stream, join it back before the end event."""
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        joined = torch.cuda.Event()
+        t0.record(stream)
+        xstream.wait_event(t0)
+        for _ in range(n_steps):
+            step(serial)
+        joined.record(xstream)
+        stream.wait_event(joined)
+        t1.record(stream)
+        return t0, t1
 
     side = torch.cuda.Stream(dev) if world > 1 else None
     done = torch.cuda.Event()
@@ -291,26 +304,27 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
         sampler.start()
-    t_begin = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
     launches0 = gswm.launch_count()
     barrier()
-    t_begin.record(stream)
-    for k in range(args.steps):
-        step()
-    t_end.record(stream)
+    t_begin, t_end = timed(args.steps)
     barrier()
     launches = gswm.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
     if world > 1:
         side.synchronize()
     n_steps_total = max(3, args.warmup) + args.steps
+    torch.cuda.synchronize(dev)
     final = (reduced if world > 1 else counters).cpu().numpy().tolist()   # accumulated over every step so far
     # every message of every step decodes exactly at sigma = 0.325
     exact = final[2] == final[3] == B * world * n_steps_total and final[0] == final[1] == B * world * L * n_steps_total
     # Per-kernel durations for the roofline block: the same launches, each kernel back to back `inst_steps` times
     # between one pair of events (so no event record or dependent-launch gap sits inside the measured interval).
     inst_steps = min(args.steps, 200)
+    # the same step with both kernels on ONE stream (no co-scheduling), for reference
+    barrier()
+    s_begin, s_end = timed(inst_steps, serial=True)
+    barrier()
+    serial_ms = s_begin.elapsed_time(s_end) / inst_steps
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     barrier()
     ev[0].record(stream)
@@ -325,10 +339,10 @@ def run_gpu_arm(args):
     embed_ms = ev[0].elapsed_time(ev[1]) / inst_steps
     extract_ms = ev[1].elapsed_time(ev[2]) / inst_steps
     clocks = sampler.stop() if rank == 0 else None
-    tm = torch.tensor([total_ms, embed_ms, extract_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([total_ms, embed_ms, extract_ms, serial_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms, embed_ms, extract_ms = tm.cpu().tolist()
+    total_ms, embed_ms, extract_ms, serial_ms = tm.cpu().tolist()
     ms_per_step = total_ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
 
@@ -385,7 +399,10 @@ def run_gpu_arm(args):
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": dom["GBps"] / peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
                 "kernels": {"embed_kernel": dict(k_embed, frac=k_embed["GBps"] / peak),
-                            "extract_kernel": dict(k_extract, frac=k_extract["GBps"] / peak)}}
+                            "extract_kernel": dict(k_extract, frac=k_extract["GBps"] / peak)},
+                # the whole co-scheduled step against the same peak: both kernels' algorithmic bytes / step time
+                "step": {"ms": ms_per_step, "GBps": 2 * lat_bytes / (ms_per_step * 1e-3) / 1e9, "algorithmic_bytes": 2 * lat_bytes,
+                         "frac": 2 * lat_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "serial_ms": serial_ms}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -404,7 +421,9 @@ def run_gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": workload_name(args), "latents_per_gpu": B, "latent_shape": [c, h, w], "msg_bits": L,
                    "l2": "inputs larger than L2 (2 x 268 MB streamed per step vs 126 MB L2)" if lat_bytes > 126e6 else
-                         "WARNING: working set fits L2", "timing": "CUDA events on the launch stream, max over ranks; per-kernel durations from %d back-to-back launches of each kernel between one event pair" % inst_steps,
+                         "WARNING: working set fits L2", "timing": "CUDA events on the launch stream (the extract stream is forked after the start event and joined before the end event), max over ranks; per-kernel durations from %d back-to-back launches of each kernel between one event pair" % inst_steps,
+                   "schedule": "embed and extract of a step run on two CUDA streams and share the SMs (FMA-bound embed next to HBM-bound extract); roofline.step.serial_ms is the same step on one stream",
+                   "uniform_source": "Philox4x32-%d, 23 bits per element" % lib.gswm_philox_rounds(),
                    "decode_exact": bool(exact), "counters": final},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

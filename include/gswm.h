@@ -95,7 +95,7 @@ int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int6
  * tile message, XOR ChaCha20 keystream, one uniform per element, z = Phi^-1((u + y) / 2), fp32 store.
  *
  * Uniform source ("gswm uniforms v2", csrc/gswm_math.cuh; restated in oracle/gs_oracle.py:gswm_uniform_ints): every
- * element gets a 23-bit integer m from Philox4x32-10 keyed by `seed`, with the counter built from the GLOBAL
+ * element gets a 23-bit integer m from Philox4x32-7 keyed by `seed`, with the counter built from the GLOBAL
  * latent index first_latent + b (so a batch sharded over ranks produces the same latents as one big batch),
  * the tile, the position and `offset` (< 2^62).  v = (m + 1/2) 2^-23; u = v for bucket bit 1, u = 1 - v for
  * bucket bit 0 (also a grid point), which makes z = +-sqrt(2) erfinv(v).
@@ -177,6 +177,9 @@ int gswm_debug_norm_ppf(const double* d_p, int64_t n, double* d_out, void* strea
 
 /* Number of kernels the library has launched in this process (all entry points); for bench.py. */
 int64_t gswm_launch_count(void);
+
+/* Rounds of the Philox4x32 generator behind gswm_embed's uniforms (7 unless built with -DGSWM_PHILOX_ROUNDS=..). */
+int gswm_philox_rounds(void);
 
 #ifdef __cplusplus
 }

@@ -211,7 +211,7 @@ def embed_scalar(message, key: bytes, nonce16: bytes, u, l_bits: int = 256) -> l
 
 # --------------------------------------------------------------------------
 # the product's counter-based uniform source (restated so the oracle can be fed
-# the identical u).  Philox4x32-10 (Salmon et al., SC'11).
+# the identical u).  Philox4x32-R (Salmon et al., SC'11); known answers are for R = 10.
 # --------------------------------------------------------------------------
 _PHILOX_M0 = np.uint64(0xD2511F53)
 _PHILOX_M1 = np.uint64(0xCD9E8D57)
@@ -235,7 +235,7 @@ def philox4x32(ctr: np.ndarray, key, rounds: int = 10) -> np.ndarray:
 
 
 GSWM_TILE = 16384          # elements per tile (32 ChaCha blocks) -- the kernels' unit of work
-GSWM_PHILOX_ROUNDS = 10
+GSWM_PHILOX_ROUNDS = 7           # csrc/gswm_math.cuh default (Philox4x32-7, the fewest Crush-resistant rounds)
 
 
 def gswm_uniform_ints(seed: int, offset: int, latent_index: int, n_elems: int,

@@ -336,6 +336,77 @@ def test_round_trip_baseline_sizes(gswm, cuda_device):
     assert list(rx.counters.cpu().numpy()) == [512 * 256, 512 * 256, 512, 512]
 
 
+def _sign_checksum(z):
+    """Order-sensitive 64-bit checksum of a batch's bucket bits (sum over elements of sign * odd weight), on the GPU."""
+    n = z[0].numel()
+    w = (torch.arange(n, device=z.device, dtype=torch.int64) * 2654435761 + 1) & 0xFFFFFFFF
+    return ((z.reshape(z.shape[0], n) >= 0).to(torch.int64) * w).sum(dim=1)
+
+
+def test_config4_sdxl_full_size(gswm, cuda_device):
+    """BASELINE config 4 at full size: 65 536 SDXL latents (4x128x128, 17.2 GB), embed + extract, checked through
+    size-independent properties: every message decodes exactly, bucket bits (a function of key/nonce/message only)
+    are identical for every latent and equal the oracle's, a 256-latent subset matches the oracle element-wise."""
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    B, shape, n = 65536, (4, 128, 128), 65536
+    if free < B * n * 4 + (8 << 30):
+        pytest.skip("needs ~26 GB of free HBM")
+    msg = gswm.pad_message("lthero", 32)
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
+    z = gswm.embed_batch(B, shape, km, 0x5EED, 0, 0, cuda_device)
+    res = gswm.extract_batch(z, km)
+    assert list(res.counters.cpu().numpy()) == [B * 256, B * 256, B, B]
+    assert bool((res.matched == 256).all())
+    # checksum of checksums: the sign pattern is the same for all latents and equals the oracle's
+    y = O.bucket_bits(O.frame_message("lthero", n, 256)[1], KEY, NONCE)[:n]
+    w = (np.arange(n, dtype=np.int64) * 2654435761 + 1) & 0xFFFFFFFF
+    expect = int((y.astype(np.int64) * w).sum())
+    cs = torch.cat([_sign_checksum(z[i:i + 4096]) for i in range(0, B, 4096)])
+    assert bool((cs == expect).all())
+    # sharding transparency at full size: latents [B-256, B) of the big batch == a 256-latent job at first_latent = B-256
+    tail = gswm.embed_batch(256, shape, km, 0x5EED, 0, B - 256, cuda_device)
+    assert torch.equal(tail, z[B - 256:])
+    sub = tail[:4].cpu().numpy().reshape(4, n)
+    for i in range(4):
+        ref = O.embed_gswm("lthero", KEY, NONCE, 0x5EED, 0, B - 256 + i, n, 256)
+        assert np.array_equal(sub[i] >= 0, ref >= 0) and rel_err(sub[i], ref).max() <= REL_TOL
+    # no two latents share their noise: |z| differs between latents (same signs, different magnitudes)
+    assert not torch.equal(z[0].abs(), z[1].abs()) and not torch.equal(z[0].abs(), z[B - 1].abs())
+
+
+def test_config5_per_latent_keys_1m(gswm, cuda_device):
+    """BASELINE config 5 at full size: 1 M SD-2.1 latents, each with its own key / nonce / message (RandomState(2025)),
+    streamed through the device API in 8 chunks of 131 072 (8.6 GB each).  Every decoded message must equal the
+    message embedded in that latent; a 64-latent subset is checked against the oracle through `cryptography`."""
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    total, chunk, shape, n, L = 1 << 20, 1 << 17, (4, 64, 64), 16384, 256
+    if free < chunk * n * 4 + (4 << 30):
+        pytest.skip("needs ~13 GB of free HBM")
+    rs = np.random.RandomState(2025)
+    keys = np.frombuffer(rs.bytes(32 * total), np.uint8).reshape(total, 32)
+    nonces = np.frombuffer(rs.bytes(16 * total), np.uint8).reshape(total, 16)
+    msgs = np.frombuffer(rs.bytes(32 * total), np.uint8).reshape(total, 32)
+    out = torch.empty((chunk, *shape), dtype=torch.float32, device=cuda_device)
+    counters = torch.zeros(4, dtype=torch.int64, device=cuda_device)
+    for c in range(total // chunk):
+        sl = slice(c * chunk, (c + 1) * chunk)
+        km = gswm.KeyMaterial.make(keys[sl], nonces[sl], msgs[sl], L)
+        gswm.embed_batch(chunk, shape, km, 2025, 0, c * chunk, cuda_device, out=out)
+        res = gswm.extract_batch(out, km, counters=counters)
+        assert torch.equal(res.messages.cpu(), torch.from_numpy(msgs[sl].copy()))
+        if c in (0, 7):
+            idx = [0, 1, chunk // 2, chunk - 1]
+            zs = out[idx].cpu().numpy().reshape(len(idx), n)
+            for j, i in enumerate(idx):
+                g = c * chunk + i
+                k, no, m = keys[g].tobytes(), nonces[g].tobytes(), msgs[g].tobytes()
+                y = O.bucket_bits(O.frame_message(m, n, L)[1], k, no, keystream=O.chacha20_keystream_lib)[:n]
+                assert np.array_equal(zs[j] >= 0, y == 1)
+                ref = O.embed_gswm(m, k, no, 2025, 0, g, n, L)
+                assert rel_err(zs[j], ref).max() <= REL_TOL
+    assert list(counters.cpu().numpy()) == [total * L, total * L, total, total]
+
+
 # ------------------------------------------------------------------------------------ host-buffer pipe
 def test_host_pipe_matches_device_api(gswm, cuda_device):
     msg = gswm.pad_message("lthero", 32)

@@ -65,6 +65,11 @@ def test_abi_basics_without_gpu(gswm):
     assert lib.gswm_chacha20_keystream(16, 16, 1, 100, 16, None) == -2
 
 
+def test_uniform_source_rounds_match_oracle(gswm):
+    # the oracle restates the library's uniform source; both must run the same number of Philox rounds
+    assert gswm._lib.lib().gswm_philox_rounds() == O.GSWM_PHILOX_ROUNDS
+
+
 def test_no_cpu_path(gswm):
     import torch
     km = gswm.KeyMaterial.make(bytes(32), bytes(16), bytes(32), 256)
