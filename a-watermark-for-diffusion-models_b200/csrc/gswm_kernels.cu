@@ -6,18 +6,15 @@
 // CTA's 256 threads then stream the tile as 16 fully coalesced 128-bit accesses per thread.
 //
 // HBM layout: latents are [n_latents][n_elems] contiguous (C-order (B,4,H/8,W/8)), 16-byte aligned;
-// keys [.][32], nonces [.][16], messages [.][msg_bits/8] are byte arrays; the shared-key workspace
-// holds one latent's worth of keystream (embed: keystream XOR tiled message), n_elems/8 bytes.
+// keys [.][32], nonces [.][16], messages [.][msg_bits/8] are byte arrays.  Keystream never touches HBM.
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include <atomic>
-#include <chrono>
 #include <cstdint>
 #include <cstdlib>
-#include <random>
 
 #include "../../include/gswm.h"
 #include "gswm_math.cuh"
@@ -91,24 +88,14 @@ chacha20_keystream_kernel(const uint8_t* __restrict__ keys, const uint8_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile keystream staging.
-//
-// per-latent keys : warp 0 of the CTA computes its tile's 32 ChaCha blocks (lane = block) straight
-//                   into shared memory.
-// shared key      : every latent needs the same keystream, so it is computed ONCE per launch, inside
-//                   the same kernel (no second launch, no dependent-launch gap): the CTAs that are
-//                   dispatched first each produce one tile-sized slice into the workspace table and
-//                   publish it with a release store of this launch's unique epoch; every CTA then
-//                   acquires the slice it needs (spin on the flag, L2 loads) into shared memory.
-//                   Producers are the lowest-numbered CTAs of the grid, which the hardware dispatches
-//                   no later than any consumer, so the wait cannot deadlock.
+// Tile keystream staging.  A CTA always computes the keystream it needs itself, into its own shared memory, one
+// ChaCha20 block per lane:
+//   shared key      : once per CTA, AHEAD of the grid dependency wait (key material is final before the call is
+//                     enqueued, gswm.h), so that behind another kernel the predecessor's tail hides it.  An earlier
+//                     version computed one table per launch in global memory and had every CTA wait on a ready flag:
+//                     4.1 us of whole-GPU idle per launch (tools/embed_trace.py) against 0 (hidden) .. 2.4 us (cold).
+//   per-latent keys : once per latent and tile, by warp 0 between two barriers.
 // ------------------------------------------------------------------------------------------------
-struct SharedTable {
-  uint32_t* table;              // [tiles_per_latent][kTileWords]
-  unsigned long long* flags;    // [tiles_per_latent], == epoch once the slice is complete
-  unsigned long long epoch;     // unique per launch
-};
-
 // lane `lane` of one warp: ChaCha block `tile*32 + lane` of stream `row`, XOR tiled message, 64 bytes to dst
 __device__ __forceinline__ void chacha_tile_lane(uint32_t* __restrict__ dst, const uint8_t* __restrict__ keys,
                                                  const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
@@ -138,48 +125,7 @@ __device__ __forceinline__ uint32_t tile_elems(int64_t n_elems, uint32_t tile) {
 // keystream words covering them (a trailing partial word / partial ChaCha block is computed whole)
 __device__ __forceinline__ uint32_t tile_words(int64_t n_elems, uint32_t tile) { return (tile_elems(n_elems, tile) + 31u) >> 5; }
 
-// Producer side (shared key): the calling WARP (all 32 lanes) writes slice `tile` of the table and publishes it.
-__device__ __forceinline__ void publish_shared_slice(const SharedTable& tab, const uint8_t* __restrict__ keys,
-                                                     const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
-                                                     int64_t n_elems, uint32_t tile, uint32_t msg_words, uint32_t tiled_words) {
-  const uint32_t lane = threadIdx.x & 31u;
-  if (lane * 16 < tile_words(n_elems, tile))
-    chacha_tile_lane(tab.table + (size_t)tile * kTileWords, keys, nonces, msg, 0, tile, lane, msg_words, tiled_words);
-  __threadfence();                                     // each lane's slice stores before the flag
-  __syncwarp();
-  if (lane == 0) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(tab.flags + tile), "l"(tab.epoch) : "memory");
-  }
-}
-
-// CTA 0 produces the whole table, warp w taking tiles w, w + 8, ...: the producer never waits on anything and is the
-// first CTA the hardware dispatches, so consumers spinning on a flag cannot deadlock.
-__device__ __forceinline__ void produce_shared_table(const SharedTable& tab, const uint8_t* __restrict__ keys,
-                                                     const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
-                                                     int64_t n_elems, uint32_t tiles, uint32_t msg_words, uint32_t tiled_words) {
-  if (blockIdx.x != 0) return;
-  for (uint32_t t = threadIdx.x >> 5; t < tiles; t += kThreads / 32)
-    publish_shared_slice(tab, keys, nonces, msg, n_elems, t, msg_words, tiled_words);
-}
-
-// Consumer side (shared key): wait for slice `tile`, copy it to shared memory (L2 loads: the producer ran on
-// another SM, L1 is not coherent).  Ends with the data visible to the whole CTA.
-__device__ __forceinline__ void acquire_shared_slice(uint32_t* __restrict__ s_ks, const SharedTable& tab, uint32_t tile,
-                                                     uint32_t words) {
-  if (threadIdx.x == 0) {
-    unsigned long long seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(tab.flags + tile) : "memory");
-      if (seen != tab.epoch) __nanosleep(100);
-    } while (seen != tab.epoch);
-  }
-  __syncthreads();
-  const uint4* src = reinterpret_cast<const uint4*>(tab.table + (size_t)tile * kTileWords);
-  if (threadIdx.x * 4 < words) reinterpret_cast<uint4*>(s_ks)[threadIdx.x] = __ldcg(src + threadIdx.x);   // whole uint4s: buffers are tile-sized
-  __syncthreads();
-}
-
-// Per-latent keys: warp 0 computes the tile in place.
+// Warp 0 computes tile `tile` of stream `row` in place (per-latent keys: row = latent; shared key: row = 0).
 __device__ __forceinline__ void compute_private_slice(uint32_t* __restrict__ s_ks, const uint8_t* __restrict__ keys,
                                                       const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
                                                       int64_t latent, uint32_t tile, uint32_t words, uint32_t msg_words,
@@ -200,7 +146,6 @@ struct EmbedArgs {
   const uint8_t* keys;
   const uint8_t* nonces;
   const uint8_t* msgs;
-  SharedTable tab;           // shared-key bucket-bit table (keystream ^ tiled message)
   float* out;
   int64_t n_elems;
   int64_t n_latents;
@@ -216,14 +161,9 @@ struct EmbedArgs {
 // Staging for the injected-uniform kernel, grid = (n_latents, tiles_per_latent): blockIdx.x = latent, blockIdx.y = tile.
 template <bool kPerLatent>
 __device__ __forceinline__ void embed_stage(uint32_t* s_ks, const EmbedArgs& a, int64_t latent, uint32_t tile, uint32_t words) {
-  if constexpr (kPerLatent) {
-    compute_private_slice(s_ks, a.keys, a.nonces, a.msgs + latent * (int64_t)a.msg_stride_bytes, latent, tile, words,
-                          a.msg_words, a.tiled_words);
-  } else {
-    if (blockIdx.x == 0 && threadIdx.x < 32)
-      publish_shared_slice(a.tab, a.keys, a.nonces, a.msgs, a.n_elems, tile, a.msg_words, a.tiled_words);
-    acquire_shared_slice(s_ks, a.tab, tile, words);
-  }
+  const int64_t row = kPerLatent ? latent : 0;
+  compute_private_slice(s_ks, a.keys, a.nonces, a.msgs + row * (int64_t)a.msg_stride_bytes, row, tile, words,
+                        a.msg_words, a.tiled_words);
 }
 
 // Sign look-up: for a byte of bucket bits, +-1.0f for the four elements of its high nibble (even float4)
@@ -307,6 +247,23 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
 #ifndef GSWM_EMBED_MINB_PER_LATENT
 #define GSWM_EMBED_MINB_PER_LATENT 6
 #endif
+// -DGSWM_TRACE: per-CTA timeline of the embed kernel (globaltimer ns at entry, after the grid dependency wait, after the
+// keystream slice is staged, at exit), read back with gswm_debug_trace_read -- tools/embed_trace.py.
+#ifdef GSWM_TRACE
+__device__ unsigned long long g_trace[2 * 4 * 8192];                  // two buffers: consecutive launches alternate
+__device__ unsigned g_trace_buf;
+__device__ __forceinline__ void trace_mark(int slot) {
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta < 8192) g_trace[(g_trace_buf & 1u) * 4 * 8192 + 4 * cta + slot] = t;
+  }
+}
+#else
+__device__ __forceinline__ void trace_mark(int) {}
+#endif
+
 template <bool kPerLatent>
 __global__ void __launch_bounds__(kThreads, kPerLatent ? GSWM_EMBED_MINB_PER_LATENT : GSWM_EMBED_MINB)
 embed_kernel(const EmbedArgs a) {
@@ -316,9 +273,20 @@ embed_kernel(const EmbedArgs a) {
   const uint32_t tiles = a.tiles_per_latent;
   const uint32_t words = tile_words(a.n_elems, tile);
   const uint32_t n_f4 = tile_elems(a.n_elems, tile) >> 2;
+  trace_mark(0);
   griddep_launch_dependents();
   build_sign_lut(s_sign);
-  griddep_wait();                                                     // nothing above touches global memory
+  if constexpr (!kPerLatent) {
+    // Shared key: this CTA's half tile needs 16 ChaCha20 blocks, once.  Half a warp computes them here, AHEAD of the
+    // grid dependency wait -- key material is final before the call is enqueued (gswm.h) -- so when the previous kernel
+    // in the stream is still draining, its tail hides this prologue; no table in global memory, no flag to spin on.
+    const uint32_t lane = threadIdx.x;
+    if (lane < 32 && (lane >> 4) == (blockIdx.y & 1u) && lane * 16 < words)
+      chacha_tile_lane(s_ks, a.keys, a.nonces, a.msgs, 0, tile, lane, a.msg_words, a.tiled_words);
+    __syncthreads();                                                  // LUT + keystream visible
+  }
+  griddep_wait();                                                     // nothing above writes global memory or reads a predecessor's output
+  trace_mark(1);
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
   const float4* my_sign = s_sign + (threadIdx.x & 1u);               // i & 1 == threadIdx.x & 1 for every float4
   const uint64_t tile_stride = 4ull * kThreads;                       // Philox counters per tile
@@ -329,10 +297,12 @@ embed_kernel(const EmbedArgs a) {
   const uint64_t g_step = (uint64_t)gridDim.x * tiles * tile_stride;
 
   if constexpr (!kPerLatent) {
-    if (blockIdx.x == 0 && (blockIdx.y & 1u) == 0 && threadIdx.x < 32)
-      publish_shared_slice(a.tab, a.keys, a.nonces, a.msgs, a.n_elems, tile, a.msg_words, a.tiled_words);
-    acquire_shared_slice(s_ks, a.tab, tile, words);                   // ends with __syncthreads(): LUT + keystream visible
+    trace_mark(2);
     const uint32_t s0 = (blockIdx.y & 1u) * 2u;                       // the launch only creates non-empty halves
+    // Static split: CTA (x, h) walks latents x, x + X, ...  (A dynamic split through per-column atomic counters was tried,
+    // because the warp schedulers share an SM unfairly and the CTAs of one launch finish anywhere between 27 and 60 us
+    // -- tools/embed_trace.py -- but same-address atomics under this kernel's store traffic complete only every ~34 ns,
+    // far too slow for one grab per latent: 67.6 us against 56.1 us.)
     if (n_f4 == kTileF4) {
       for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
         embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4);
@@ -344,6 +314,7 @@ embed_kernel(const EmbedArgs a) {
         if ((s0 + 1) * 4 * kThreads < n_f4) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4);
       }
     }
+    trace_mark(3);
   } else {
     for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
       __syncthreads();                                                // previous latent's readers are done with s_ks (first pass: LUT built)
@@ -401,7 +372,6 @@ struct ExtractArgs {
   const uint8_t* keys;
   const uint8_t* nonces;
   const uint8_t* msgs;        // reference messages (may be null)
-  SharedTable tab;            // shared-key keystream table
   const void* z;
   uint8_t* msg_out;
   uint16_t* counts;
@@ -553,17 +523,19 @@ extract_kernel(const ExtractArgs a) {
     s_matched = 0;
   }
   for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) s_cnt[p] = 0;
+  if constexpr (!kPerLatent) {
+    // Shared key, a latent's whole keystream fits the cache: every CTA computes it once, warp w taking tiles w, w + 8, ..,
+    // ahead of the grid dependency wait (key material is final before the call is enqueued, gswm.h).
+    for (uint32_t t = threadIdx.x >> 5; t < a.ks_cache_tiles; t += kThreads / 32) {
+      const uint32_t lane = threadIdx.x & 31u;
+      if (lane * 16 < tile_words(a.n_elems, t))
+        chacha_tile_lane(s_ks_all + t * kTileWords, a.keys, a.nonces, nullptr, 0, t, lane, 0, 0);
+    }
+  }
   __syncthreads();
-  griddep_wait();                                                     // nothing above touches global memory
+  griddep_wait();                                                     // nothing above writes global memory or reads a predecessor's output
   if (threadIdx.x == 0) {
     for (int64_t q = 0; q < kStages - 1; ++q) issue(q);               // kStages-1 chunks in flight from the start
-  }
-  if constexpr (!kPerLatent)                    // CTA 0 produces the shared keystream table for the whole grid
-    produce_shared_table(a.tab, a.keys, a.nonces, nullptr, a.n_elems, a.tiles_per_latent, 0, 0);
-
-  if constexpr (!kPerLatent) {                  // a latent's whole keystream fits the cache: stage it once per CTA
-    for (uint32_t t = 0; t < a.ks_cache_tiles; ++t)
-      acquire_shared_slice(s_ks_all + t * kTileWords, a.tab, t, tile_words(a.n_elems, t));
   }
 
   unsigned long long acc_matched = 0, acc_exact = 0, acc_msgs = 0;   // thread 0 only; flushed once per CTA
@@ -584,8 +556,7 @@ extract_kernel(const ExtractArgs a) {
       uint32_t* s_ks = ks_resident ? s_ks_all + tile * kTileWords : s_ks_all;
       if (chunk_in_tile == 0 && !ks_resident) {   // new tile: stage its keystream (both paths end with a barrier)
         const uint32_t words = tile_words(a.n_elems, tile);
-        if constexpr (kPerLatent) compute_private_slice(s_ks, a.keys, a.nonces, nullptr, latent, tile, words, 0, 0);
-        else acquire_shared_slice(s_ks, a.tab, tile, words);
+        compute_private_slice(s_ks, a.keys, a.nonces, nullptr, kPerLatent ? latent : 0, tile, words, 0, 0);
       }
       const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
       const int64_t e0 = (int64_t)within * kChunkElems;
@@ -723,34 +694,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 static uint32_t tiles_of(int64_t n_elems) { return (uint32_t)((n_elems + kTileElems - 1) / kTileElems); }
 
-static size_t shared_workspace_bytes(int64_t n_elems) {
-  const size_t tiles = tiles_of(n_elems);
-  return tiles * (size_t)kTileWords * 4 + ((tiles * 8 + 15) & ~(size_t)15);
-}
-
-// A value no earlier launch (and, with overwhelming probability, no stale memory) carries.
-static unsigned long long next_epoch() {
-  static std::atomic<unsigned long long> epoch{[] {
-    std::random_device rd;
-    return ((unsigned long long)rd() << 32) ^ (unsigned long long)rd() ^
-           (unsigned long long)std::chrono::steady_clock::now().time_since_epoch().count();
-  }()};
-  unsigned long long e;
-  do { e = epoch.fetch_add(1, std::memory_order_relaxed) + 1; } while (e == 0);
-  return e;
-}
-
-static int make_shared_table(const gswm_job* job, void* d_workspace, SharedTable* tab) {
-  *tab = SharedTable{nullptr, nullptr, 0};
-  if (job->per_latent) return GSWM_OK;
-  if (!d_workspace) return GSWM_E_WORKSPACE;
-  if (!aligned16(d_workspace)) return GSWM_E_ALIGN;
-  const size_t tiles = tiles_of(job->n_elems);
-  tab->table = reinterpret_cast<uint32_t*>(d_workspace);
-  tab->flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_workspace) + tiles * (size_t)kTileWords * 4);
-  tab->epoch = next_epoch();
-  return GSWM_OK;
-}
+static unsigned halves_of(int64_t n_elems) { return (unsigned)((n_elems / 4 + 8 * kThreads - 1) / (8 * kThreads)); }
 
 static EmbedArgs make_embed_args(const gswm_job* job) {
   EmbedArgs a{};
@@ -862,7 +806,7 @@ const char* gswm_strerror(int code) {
     case GSWM_E_MSGLEN: return "gswm: msg_bits must be a positive multiple of 32, <= n_elems (and divide it for extract)";
     case GSWM_E_DTYPE: return "gswm: unknown element type";
     case GSWM_E_RANGE: return "gswm: size out of range";
-    case GSWM_E_WORKSPACE: return "gswm: shared-key job needs a workspace of gswm_workspace_bytes()";
+    case GSWM_E_WORKSPACE: return "gswm: workspace too small (reserved; no current entry point returns it)";
     case GSWM_E_ALIGN: return "gswm: device pointer not 16-byte aligned";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gswm: unknown error";
   }
@@ -893,9 +837,19 @@ int64_t gswm_launch_count(void) { return g_launches.load(std::memory_order_relax
 
 int gswm_philox_rounds(void) { return GSWM_PHILOX_ROUNDS; }
 
+#ifdef GSWM_TRACE
+int gswm_debug_trace_read(unsigned long long* h_out, int buf) {      // h_out[4 * 8192]
+  return (int)cudaMemcpyFromSymbol(h_out, g_trace, sizeof(unsigned long long) * 4 * 8192, sizeof(unsigned long long) * 4 * 8192 * (size_t)(buf & 1));
+}
+int gswm_debug_trace_select(int buf, void* stream) {                 // stream-ordered: later launches write buffer `buf`
+  const unsigned b = (unsigned)buf;
+  return (int)cudaMemcpyToSymbolAsync(g_trace_buf, &b, sizeof(b), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+}
+#endif
+
 size_t gswm_workspace_bytes(const gswm_job* job) {
-  if (!job || job->per_latent || job->n_elems <= 0) return 0;
-  return shared_workspace_bytes(job->n_elems);
+  (void)job;                                                          // no entry point needs scratch memory any more
+  return 0;
 }
 
 int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int64_t n_streams,
@@ -925,7 +879,6 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   EmbedArgs a = make_embed_args(job);
-  if ((rc = make_shared_table(job, d_workspace, &a.tab))) return rc;
   a.out = d_out;
   a.first_latent = first_latent;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
@@ -934,9 +887,9 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
     a.rk.k[2 * r] = a.seed_lo + (uint32_t)r * 0x9E3779B9u;
     a.rk.k[2 * r + 1] = a.seed_hi + (uint32_t)r * 0xBB67AE85u;
   }
-  const unsigned halves = (unsigned)((job->n_elems / 4 + 8 * kThreads - 1) / (8 * kThreads));   // non-empty half tiles
+  (void)d_workspace;                                                  // reserved (see gswm_workspace_bytes)
   rc = job->per_latent ? launch_embed(embed_kernel<true>, a, a.tiles_per_latent, false, st)
-                       : launch_embed(embed_kernel<false>, a, halves, true, st);
+                       : launch_embed(embed_kernel<false>, a, halves_of(job->n_elems), true, st);   // Y = non-empty half tiles
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return rc;
 }
@@ -950,7 +903,7 @@ int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_la
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   EmbedArgs a = make_embed_args(job);
-  if ((rc = make_shared_table(job, d_workspace, &a.tab))) return rc;
+  (void)d_workspace;                                                  // not needed by this entry point
   const dim3 grid((unsigned)job->n_latents, tiles_of(job->n_elems));
   const int upl = u_per_latent ? 1 : 0;
   if (out_dtype == GSWM_F32) {
@@ -977,7 +930,7 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   ExtractArgs a{};
-  if ((rc = make_shared_table(job, d_workspace, &a.tab))) return rc;
+  (void)d_workspace;                                                  // not needed by this entry point
   a.keys = job->d_keys; a.nonces = job->d_nonces; a.msgs = job->d_msgs;
   a.z = d_z; a.msg_out = d_msg_out; a.counts = d_counts; a.matched = d_matched;
   a.counters = reinterpret_cast<unsigned long long*>(d_counters);

@@ -33,7 +33,6 @@ struct Slot {
   cudaEvent_t done = nullptr;  // recorded after the chunk's kernel (its outputs are then visible in the staging)
   void* d_in = nullptr;        // z (extract) or u (injected embed): chunk * max_elems * 8 bytes
   void* d_out = nullptr;       // latents out (embed): chunk * max_elems * 8 bytes
-  void* d_ws = nullptr;        // gswm_workspace_bytes for max_elems
   // pinned, device-visible host staging the extract kernel writes its small outputs into
   uint8_t* h_msg_out = nullptr;   // chunk * kMaxMsgBytes
   uint16_t* h_counts = nullptr;   // chunk * 8192
@@ -165,9 +164,6 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
   p->max_elems = max_elems;
   p->chunk = max_latents_per_chunk;
   const size_t lat_bytes = (size_t)p->chunk * (size_t)max_elems * 8;
-  gswm_job probe{};
-  probe.n_elems = max_elems;
-  const size_t ws_bytes = gswm_workspace_bytes(&probe);
   int rc = 0;
   auto A = [&](void** ptr, size_t bytes) {
     if (rc == 0) rc = (int)cudaMalloc(ptr, bytes);
@@ -180,7 +176,6 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
     if (rc == 0) rc = (int)cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     A(&s.d_in, lat_bytes);
     A(&s.d_out, lat_bytes);
-    A(&s.d_ws, ws_bytes);
     H((void**)&s.h_msg_out, (size_t)p->chunk * kMaxMsgBytes);
     H((void**)&s.h_counts, (size_t)p->chunk * 8192 * sizeof(uint16_t));
     H((void**)&s.h_matched, (size_t)p->chunk * sizeof(int32_t));
@@ -200,7 +195,7 @@ void gswm_pipe_destroy(gswm_pipe* p) {
   cudaSetDevice(p->device);
   for (auto& s : p->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_ws);
+    cudaFree(s.d_in); cudaFree(s.d_out);
     cudaFreeHost(s.h_msg_out); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_matched);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -227,7 +222,7 @@ int gswm_pipe_embed(gswm_pipe* p, const gswm_host_job* job, uint64_t seed, uint6
     const int64_t n = std::min(p->chunk, job->n_latents - first);
     gswm_job dj;
     chunk_job(job, dk, first, n, &dj);
-    if ((rc = gswm_embed(&dj, seed, offset, first_latent + first, (float*)s.d_out, s.d_ws, s.stream))) break;
+    if ((rc = gswm_embed(&dj, seed, offset, first_latent + first, (float*)s.d_out, nullptr, s.stream))) break;
     rc = (int)cudaMemcpyAsync(reinterpret_cast<char*>(h_out) + (size_t)first * row_bytes, s.d_out, (size_t)n * row_bytes,
                               cudaMemcpyDeviceToHost, s.stream);
   }
@@ -254,7 +249,7 @@ int gswm_pipe_embed_injected(gswm_pipe* p, const gswm_host_job* job, const doubl
     chunk_job(job, dk, first, n, &dj);
     const char* u_src = reinterpret_cast<const char*>(h_u) + (u_per_latent ? (size_t)first * u_row : 0);
     if ((rc = (int)cudaMemcpyAsync(s.d_in, u_src, (u_per_latent ? (size_t)n : 1) * u_row, cudaMemcpyHostToDevice, s.stream))) break;
-    if ((rc = gswm_embed_injected(&dj, (const double*)s.d_in, u_per_latent, s.d_out, out_dtype, s.d_ws, s.stream))) break;
+    if ((rc = gswm_embed_injected(&dj, (const double*)s.d_in, u_per_latent, s.d_out, out_dtype, nullptr, s.stream))) break;
     rc = (int)cudaMemcpyAsync(reinterpret_cast<char*>(h_out) + (size_t)first * out_row, s.d_out, (size_t)n * out_row,
                               cudaMemcpyDeviceToHost, s.stream);
   }
@@ -291,7 +286,7 @@ int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, i
                                    cudaMemcpyHostToDevice, s.stream))) break;
     // small outputs: the kernel stores them straight into the slot's mapped host staging (no copy-engine work)
     if ((rc = gswm_extract(&dj, s.d_in, z_dtype, s.h_msg_out, h_counts ? s.h_counts : nullptr,
-                           want_matched ? s.h_matched : nullptr, p->d_counters, s.d_ws, s.stream))) break;
+                           want_matched ? s.h_matched : nullptr, p->d_counters, nullptr, s.stream))) break;
     if ((rc = (int)cudaEventRecord(s.done, s.stream))) break;
     s.pending_first = first;
     s.pending_n = n;

@@ -209,7 +209,26 @@ def ncu_traffic(kernel):
         return None
 
 
+def gpu_local_cpus(torch, index):
+    """CPUs of the NUMA node the GPU's PCIe slot hangs off, intersected with this process's affinity (empty set if unknown)."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return set()
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus & os.sched_getaffinity(0)
+    except Exception:  # noqa: BLE001
+        return set()
+
+
 def run_gpu_arm(args):
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only
     import torch
     import torch.distributed as dist
 
@@ -350,6 +369,11 @@ def run_gpu_arm(args):
     # Two pipes (one per direction) driven from two host threads: the embed side's D2H and the extract side's H2D
     # use the two directions of the PCIe link at the same time (ctypes releases the GIL during the calls).
     import threading
+    # host buffers and the pipe's staging live on the GPU's own NUMA node (first touch happens under this affinity)
+    affinity0 = os.sched_getaffinity(0)
+    local_cpus = gpu_local_cpus(torch, local)
+    if local_cpus:
+        os.sched_setaffinity(0, local_cpus)
     pipe_e = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, B))
     pipe_x = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, B))
     h_out = torch.empty((B, *shape), dtype=torch.float32).pin_memory()
@@ -383,6 +407,7 @@ def run_gpu_arm(args):
     d2h = B * n * 4 + B * (L // 8) + B * 4 + 32
     pipe_e.close()
     pipe_x.close()
+    os.sched_setaffinity(0, affinity0)
 
     if world > 1:
         dist.barrier()
@@ -428,7 +453,8 @@ def run_gpu_arm(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "decode_exact": bool(e2e_ok),
-                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), %d-latent chunks, 2 slots each" % min(E2E_CHUNK, B)},
+                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), %d-latent chunks, 2 slots each" % min(E2E_CHUNK, B),
+                "numa_local_cpus": len(local_cpus)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

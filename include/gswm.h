@@ -36,7 +36,7 @@ enum {
   GSWM_E_MSGLEN = -3,      /* msg_bits not a positive multiple of 32, > n_elems, or (extract) not dividing n_elems */
   GSWM_E_DTYPE = -4,       /* unknown element type code */
   GSWM_E_RANGE = -5,       /* a size exceeds what the kernels index */
-  GSWM_E_WORKSPACE = -6,   /* shared-key job without a workspace of gswm_workspace_bytes() */
+  GSWM_E_WORKSPACE = -6,   /* workspace smaller than gswm_workspace_bytes() (reserved: no entry point needs one today) */
   GSWM_E_ALIGN = -7        /* latent/workspace pointer not 16-byte aligned, or key/nonce/message not 4-byte aligned */
 };
 
@@ -54,6 +54,12 @@ enum { GSWM_F32 = 0, GSWM_F16 = 1, GSWM_BF16 = 2, GSWM_F64 = 3 };
  * the padded/truncated `k` of gs_insert.py:9-20 (nodes.py:68-76, v1.5.2:29-47 for other framings).
  * The message is tiled n_elems/msg_bits times; a remainder (msg_bits not dividing n_elems, embed only)
  * carries plaintext zero, as nodes.py:79-87 does.
+ *
+ * Ordering: d_keys / d_nonces / d_msgs must hold their final contents when the call is ENQUEUED behind a kernel
+ * that uses programmatic dependent launch (every gswm kernel does): the kernels read key material ahead of the
+ * grid dependency wait so that the ChaCha20 prologue overlaps the previous kernel's tail.  Key material written by
+ * a memcpy or by an ordinary kernel earlier in the same stream is ordered as usual.  Latents and all outputs are
+ * only touched after the wait.
  */
 typedef struct gswm_job {
   int64_t n_latents;
@@ -77,7 +83,9 @@ enum {
 int gswm_abi_version(void);
 const char* gswm_strerror(int code);
 
-/* Bytes of device workspace a shared-key job needs (0 for per_latent jobs). */
+/* Bytes of device scratch memory a job needs behind the `d_workspace` arguments below.  Currently always 0 -- every
+ * CTA computes the keystream it needs into its own shared memory -- and `d_workspace` may be NULL; the argument is
+ * kept so that a future kernel that needs scratch memory does not change the ABI. */
 size_t gswm_workspace_bytes(const gswm_job* job);
 
 /*
@@ -99,7 +107,7 @@ int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int6
  * latent index first_latent + b (so a batch sharded over ranks produces the same latents as one big batch),
  * the tile, the position and `offset` (< 2^62).  v = (m + 1/2) 2^-23; u = v for bucket bit 1, u = 1 - v for
  * bucket bit 0 (also a grid point), which makes z = +-sqrt(2) erfinv(v).
- * d_out: [n_latents][n_elems] fp32, 16-byte aligned.  d_workspace: gswm_workspace_bytes(job).
+ * d_out: [n_latents][n_elems] fp32, 16-byte aligned.  d_workspace: gswm_workspace_bytes(job) bytes (0: may be NULL).
  */
 int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent,
                float* d_out, void* d_workspace, void* stream);

@@ -48,7 +48,7 @@ def test_abi_basics_without_gpu(gswm):
     for code in range(-7, 0):
         assert gswm._lib.strerror(code).startswith("gswm:")
     job = gswm._lib.Job(3, 16384, 256, 0, None, None, None)
-    assert lib.gswm_workspace_bytes(C.byref(job)) == 2048 + 16          # one tile of keystream + its ready flag
+    assert lib.gswm_workspace_bytes(C.byref(job)) == 0                  # keystream lives in shared memory only
     job.per_latent = 1
     assert lib.gswm_workspace_bytes(C.byref(job)) == 0
     # argument validation happens before any CUDA call
