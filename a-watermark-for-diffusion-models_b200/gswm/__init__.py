@@ -12,9 +12,10 @@ every compute call needs a CUDA device and the built library.
 from . import _lib
 from ._lib import GswmError, build, launch_count
 from .codec import (DEFAULT_KEY_HEX, DEFAULT_NONCE_HEX, ExtractResult, HostPipe, KeyMaterial, chacha20_keystream,
-                    choose_watermark_length, embed_batch, embed_batch_injected, extract_batch, pad_message,
+                    choose_watermark_length, embed_batch, embed_batch_injected, embed_extract_batch, extract_batch,
+                    pad_message,
                     resolve_key_nonce)
 
 __all__ = ["GswmError", "build", "launch_count", "DEFAULT_KEY_HEX", "DEFAULT_NONCE_HEX", "ExtractResult", "HostPipe",
            "KeyMaterial", "chacha20_keystream", "choose_watermark_length", "embed_batch", "embed_batch_injected",
-           "extract_batch", "pad_message", "resolve_key_nonce", "_lib"]
+           "embed_extract_batch", "extract_batch", "pad_message", "resolve_key_nonce", "_lib"]

@@ -336,6 +336,22 @@ def test_round_trip_baseline_sizes(gswm, cuda_device):
     assert list(rx.counters.cpu().numpy()) == [512 * 256, 512 * 256, 512, 512]
 
 
+def test_coscheduled_step_matches_separate_calls(gswm, cuda_device):
+    """embed_extract_batch (embed and extract on two streams, sharing the SMs) returns exactly what the two calls
+    return one after the other -- including when it is called repeatedly with the results consumed at once."""
+    msg = gswm.pad_message("lthero", 32)
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
+    z0 = gswm.embed_batch(1024, (4, 64, 64), km, 11, 0, 0, cuda_device)
+    noisy = z0 + 0.8 * torch.randn(z0.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(3))
+    want_z = gswm.embed_batch(1024, (4, 64, 64), km, 12, 0, 5000, cuda_device)
+    want = gswm.extract_batch(noisy, km, want_counts=True)
+    for _ in range(4):
+        z, res = gswm.embed_extract_batch(1024, (4, 64, 64), km, 12, noisy, first_latent=5000, want_counts=True)
+        assert torch.equal(z, want_z)
+        assert torch.equal(res.messages, want.messages) and torch.equal(res.counts, want.counts)
+        assert torch.equal(res.matched, want.matched) and torch.equal(res.counters, want.counters)
+
+
 def _sign_checksum(z):
     """Order-sensitive 64-bit checksum of a batch's bucket bits (sum over elements of sign * odd weight), on the GPU."""
     n = z[0].numel()
