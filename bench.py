@@ -227,8 +227,10 @@ def gpu_local_cpus(torch, index):
 
 
 def run_gpu_arm(args):
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only
+    # stdout carries the one JSON line only: libraries that printf to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -457,7 +459,7 @@ def run_gpu_arm(args):
                 "numa_local_cpus": len(local_cpus)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -64,7 +64,7 @@ s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 msgs = torch.empty((B, L // 8), dtype=torch.uint8, device=dev)
 matched = torch.empty((B,), dtype=torch.int32, device=dev)
 counters = torch.zeros(4, dtype=torch.int64, device=dev)
-ws2 = torch.empty_like(dj.workspace)
+ws2 = None   # no entry point needs scratch memory (gswm_workspace_bytes == 0)
 
 
 def zc_embed(sync=True):
@@ -75,7 +75,7 @@ def zc_embed(sync=True):
 
 def zc_extract(sync=True):
     gswm._lib.check(lib.gswm_extract(C.byref(dj.job), h_in.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
-                                     counters.data_ptr(), ws2.data_ptr(), s2.cuda_stream), "extract")
+                                     counters.data_ptr(), None, s2.cuda_stream), "extract")
     if sync:
         s2.synchronize()
 
