@@ -395,6 +395,13 @@ struct ExtractArgs {
 #endif
 // A chunk is a fixed number of BYTES (what the memory system has in flight per CTA is what matters): 8192 fp32 or
 // 16384 fp16 / bf16 elements -- half a tile or a whole tile.
+// Ring depth: fp32 input 3 stages (96 KB -> 2 CTAs per SM), 16-bit input 2 stages (64 KB -> 3 CTAs per SM).  Alone, both
+// shapes keep ~192 KB per SM in flight and fp32 runs within 2 % of each other (41.4 / 42.2 us); 16-bit input is bound by
+// the consumer warps and wants the third CTA (22.5 against 25.1 us), and so do per-latent keys, where warp 0's ChaCha20
+// rounds stall a CTA once per tile (45.3 against 52.3 us).  But next to the embed kernel (the co-scheduled
+// step, bench.py) only one or two extract CTAs find room on an SM, and then the bytes EACH of them keeps in flight
+// decide how much of the idle HBM bandwidth gets used: 87.2 us per step with 3 stages against 93.1 us with 2
+// (tools/cobench.py).  -DGSWM_STAGES=n overrides both.
 constexpr int kStageBytes = GSWM_CHUNK_BYTES;
 template <typename T>
 struct Chunk {
@@ -402,10 +409,15 @@ struct Chunk {
   static constexpr int kPerTile = kTileElems / kElems;
   static_assert(kPerTile >= 1 && kPerTile * kElems == kTileElems, "a chunk must divide a tile");
 };
-#ifndef GSWM_STAGES
-#define GSWM_STAGES 2
+template <typename T, bool kPerLatent>
+struct Ring {
+#ifdef GSWM_STAGES
+  static constexpr int kStages = GSWM_STAGES;
+#else
+  static constexpr int kStages = (sizeof(T) == 4 && !kPerLatent) ? 3 : 2;
 #endif
-constexpr int kStages = GSWM_STAGES;
+  static constexpr int kMinBlocks = kStages * kStageBytes > 72 * 1024 ? 2 : GSWM_EXTRACT_MINB;
+};
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -479,8 +491,9 @@ template <>
 struct NegatedBits<__nv_bfloat16> : NegatedBits16<__nv_bfloat162, 0xA4A0u> {};
 
 template <typename T, bool kPerLatent, bool kPow2>
-__global__ void __launch_bounds__(kThreads, GSWM_EXTRACT_MINB)
+__global__ void __launch_bounds__(kThreads, (Ring<T, kPerLatent>::kMinBlocks))
 extract_kernel(const ExtractArgs a) {
+  constexpr int kStages = Ring<T, kPerLatent>::kStages;
   constexpr int kChunkElems = Chunk<T>::kElems;
   constexpr int kChunksPerTile = Chunk<T>::kPerTile;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -944,7 +957,9 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   a.chunks_per_latent = (uint32_t)((job->n_elems + chunk_elems - 1) / chunk_elems);
   const bool pow2 = (1024 % job->msg_bits) == 0;
   a.ks_cache_tiles = (!job->per_latent && a.tiles_per_latent <= 8) ? a.tiles_per_latent : 0;
-  const size_t smem = (size_t)kStages * kStageBytes +
+  const int stages = z_dtype != GSWM_F32 ? Ring<__half, false>::kStages
+                                         : (job->per_latent ? Ring<float, true>::kStages : Ring<float, false>::kStages);
+  const size_t smem = (size_t)stages * kStageBytes +
                       (size_t)((a.ks_cache_tiles ? a.ks_cache_tiles : 1u) * kTileWords + job->msg_bits) * sizeof(uint32_t);
   if (z_dtype == GSWM_F32) rc = launch_extract<float>(a, job->per_latent != 0, pow2, smem, st);
   else if (z_dtype == GSWM_F16) rc = launch_extract<__half>(a, job->per_latent != 0, pow2, smem, st);
