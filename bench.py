@@ -80,19 +80,29 @@ def _cpu_worker(job):
     return time.perf_counter() - t0, ok
 
 
-def cpu_pairs_per_second(n_elems, msg_bits, pairs_per_worker, cores):
-    """All `cores` workers run `pairs_per_worker` pairs concurrently; returns (pairs/s, total pairs, all decoded ok)."""
+def cpu_pool(cores):
+    """One worker process per host core, started (and warmed: imports done) once, so that a step times the reference's
+    arithmetic and not process start-up."""
     import multiprocessing as mp
 
-    ctx = mp.get_context("fork")
-    jobs = [(pairs_per_worker, n_elems, msg_bits, 1000 + i) for i in range(cores)]
-    t0 = time.perf_counter()
     if cores == 1:
-        res = [_cpu_worker(jobs[0])]
-    else:
-        with ctx.Pool(cores) as pool:
-            res = pool.map(_cpu_worker, jobs)
+        return None
+    pool = mp.get_context("fork").Pool(cores)
+    pool.map(_cpu_worker, [(1, 16384, 256, i) for i in range(cores)])
+    return pool
+
+
+def cpu_pairs_per_second(n_elems, msg_bits, pairs_per_worker, cores, pool=None):
+    """All `cores` workers run `pairs_per_worker` pairs concurrently; returns (pairs/s, total pairs, all decoded ok)."""
+    jobs = [(pairs_per_worker, n_elems, msg_bits, 1000 + i) for i in range(cores)]
+    own = pool is None and cores > 1
+    if own:
+        pool = cpu_pool(cores)
+    t0 = time.perf_counter()
+    res = [_cpu_worker(jobs[0])] if cores == 1 else pool.map(_cpu_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
+    if own:
+        pool.close()
     total = pairs_per_worker * cores
     return total / wall, total, sum(r[1] for r in res) == total
 
@@ -114,16 +124,19 @@ def run_reference_arm(args):
     # each step: a bounded sample so that warmup + steps stays within ~2 minutes
     budget_per_step = min(6.0, 100.0 / max(1, args.steps + args.warmup))
     ppw = max(2, int(budget_per_step / per_pair))
+    pool = cpu_pool(cores)
     for _ in range(args.warmup):
-        cpu_pairs_per_second(n, args.msg_bits, max(1, ppw // 4), cores)
+        cpu_pairs_per_second(n, args.msg_bits, max(1, ppw // 4), cores, pool)
     t0 = time.perf_counter()
     total = 0
     ok = True
     for _ in range(args.steps):
-        _, tp, o = cpu_pairs_per_second(n, args.msg_bits, ppw, cores)
+        _, tp, o = cpu_pairs_per_second(n, args.msg_bits, ppw, cores, pool)
         total += tp
         ok &= o
     wall = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
     value = total / wall
     sample = f"{ppw * cores} embed+extract pairs per step ({ppw} per core x {cores} processes), vectorised numpy/scipy/cryptography port of the reference"
     line = {

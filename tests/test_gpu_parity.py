@@ -330,7 +330,22 @@ def test_round_trip_baseline_sizes(gswm, cuda_device):
     sub = noisy[:16].cpu().numpy()
     for i in range(16):
         assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(sub[i], KEY, NONCE, 256))
-    del z, noisy
+    # sigma = 4.3 regime: ~90 % of the DECODED bits survive; counts / messages / matched bits of a
+    # subset bit-exact against the oracle, and the batch counters equal the sum of the per-latent figures
+    heavy = (z + 4.3 * torch.randn(z.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(7))).clamp(max=8.0)
+    res = gswm.extract_batch(heavy, km, want_counts=True)
+    assert 0.88 < res.bit_accuracy() < 0.92
+    c = res.counters.cpu().numpy()
+    assert int(c[0]) == int(res.matched.sum()) and int(c[1]) == 4096 * 256 and int(c[3]) == 4096
+    assert int(c[2]) == int((res.matched == 256).sum())
+    sub = heavy[:16].cpu().numpy()
+    ref_bits = np.unpackbits(np.frombuffer(msg, np.uint8))
+    for i in range(16):
+        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(sub[i], KEY, NONCE, 256))
+        bits = O.recover_message_bits(sub[i], KEY, NONCE, 256)
+        assert O.bits_to_bytes(bits) == res.messages[i].cpu().numpy().tobytes()
+        assert int(res.matched[i]) == int((bits == ref_bits).sum())
+    del z, noisy, heavy
     zx = gswm.embed_batch(512, (4, 128, 128), km, 1, 0, 0, cuda_device)
     rx = gswm.extract_batch(zx, km)
     assert list(rx.counters.cpu().numpy()) == [512 * 256, 512 * 256, 512, 512]
