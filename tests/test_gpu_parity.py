@@ -367,6 +367,33 @@ def test_coscheduled_step_matches_separate_calls(gswm, cuda_device):
         assert torch.equal(res.matched, want.matched) and torch.equal(res.counters, want.counters)
 
 
+def test_back_to_back_jobs_with_changing_keys(gswm, cuda_device):
+    """Programmatic dependent launch lets a kernel's prologue (its ChaCha20 keystream) run under the previous kernel's
+    tail.  60 jobs with fresh key material, alternating shapes and both key modes, enqueued without any host sync,
+    must each decode to their own message and reproduce the oracle's bucket bits."""
+    rs = np.random.RandomState(4242)
+    shapes = [((4, 64, 64), 256), ((4, 128, 128), 256), ((4, 8, 16), 32), ((4, 96, 64), 96)]
+    jobs = []
+    for it in range(60):
+        shape, L = shapes[it % len(shapes)]
+        b = int(rs.randint(1, 700))
+        per = it % 5 == 4
+        rows = b if per else 1
+        key, nonce, msg = rs.bytes(32 * rows), rs.bytes(16 * rows), rs.bytes((L // 8) * rows)
+        km = gswm.KeyMaterial.make(key, nonce, msg, L)
+        z = gswm.embed_batch(b, shape, km, it, 0, 0, cuda_device)
+        res = gswm.extract_batch(z, km)
+        jobs.append((shape, L, b, per, key, nonce, msg, z[:1].clone(), res))
+    torch.cuda.synchronize()
+    for shape, L, b, per, key, nonce, msg, z0, res in jobs:
+        want = msg if per else msg * b
+        assert res.messages.cpu().numpy().tobytes() == want
+        assert list(res.counters.cpu().numpy()) == [b * L, b * L, b, b]
+        n = int(np.prod(shape))
+        y = O.bucket_bits(O.frame_message(msg[:L // 8], n, L)[1], key[:32], nonce[:16])[:n]
+        assert np.array_equal(z0.cpu().numpy().reshape(-1) >= 0, y == 1)
+
+
 def _sign_checksum(z):
     """Order-sensitive 64-bit checksum of a batch's bucket bits (sum over elements of sign * odd weight), on the GPU."""
     n = z[0].numel()
