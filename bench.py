@@ -239,6 +239,24 @@ def gpu_local_cpus(torch, index):
         return set()
 
 
+def ncu_pipe_summary(kernel):
+    """Issue / pipe utilisation of `kernel` from the committed ncu --set full capture (profiles/), for the roofline block:
+    the embed kernel is bound by the FMA pipes, not by HBM, and these are the numbers that say so."""
+    try:
+        with open(os.path.join(ROOT, "profiles", f"r01b_{kernel.split('_')[0]}_ncu_summary.json")) as f:
+            k = json.load(f)["kernels"][0]
+        pick = {"issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "fma_heavy_pipe_pct": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                "alu_pipe_pct": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+                "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                "duration_us_under_ncu": "gpu__time_duration.sum"}
+        out = {a: round(float(k[b]["value"]), 2) for a, b in pick.items()}
+        out["source"] = f"profiles/r01b_{kernel.split('_')[0]}_ncu_summary.json (cold, serialised launch)"
+        return out
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_gpu_arm(args):
     # stdout carries the one JSON line only: libraries that printf to fd 1 (NCCL's version banner) go to stderr
     sys.stdout.flush()
@@ -438,8 +456,8 @@ def run_gpu_arm(args):
     dom_name, dom = ("embed_kernel", k_embed) if embed_ms >= extract_ms else ("extract_kernel", k_extract)
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": dom["GBps"] / peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
-                "kernels": {"embed_kernel": dict(k_embed, frac=k_embed["GBps"] / peak),
-                            "extract_kernel": dict(k_extract, frac=k_extract["GBps"] / peak)},
+                "kernels": {"embed_kernel": dict(k_embed, frac=k_embed["GBps"] / peak, ncu=ncu_pipe_summary("embed_kernel")),
+                            "extract_kernel": dict(k_extract, frac=k_extract["GBps"] / peak, ncu=ncu_pipe_summary("extract_kernel"))},
                 # the whole co-scheduled step against the same peak: both kernels' algorithmic bytes / step time
                 "step": {"ms": ms_per_step, "GBps": 2 * lat_bytes / (ms_per_step * 1e-3) / 1e9, "algorithmic_bytes": 2 * lat_bytes,
                          "frac": 2 * lat_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "serial_ms": serial_ms}}
