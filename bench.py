@@ -319,17 +319,11 @@ def run_gpu_arm(args):
         gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
         gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
                                          counters.data_ptr(), ws2p, sp if serial else xp), "gswm_extract")
-        if world > 1 and not serial:
-            # the only collective: 32 bytes of bit-match counters, all-reduced on a side stream so it overlaps the
-            # next step (counters keep accumulating locally; `reduced` is the cross-rank total so far)
-            done.record(xstream)
-            with torch.cuda.stream(side):
-                side.wait_event(done)
-                reduced.copy_(counters)
-                dist.all_reduce(reduced)
 
-    def timed(n_steps, serial=False):
-        """Device time of n_steps steps: fork the extract stream off the launch stream, join it back before the end event."""
+    def timed(n_steps, serial=False, reduce=True):
+        """Device time of n_steps steps: fork the extract stream off the launch stream, join it back before the end event.
+        The path's only collective -- the FINAL all-reduce of the 4 int64 bit-match counters the extract kernels have been
+        accumulating (north_star) -- runs once, after the last step and inside the timed region."""
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         joined = torch.cuda.Event()
         t0.record(stream)
@@ -338,11 +332,12 @@ def run_gpu_arm(args):
             step(serial)
         joined.record(xstream)
         stream.wait_event(joined)
+        if world > 1 and reduce:
+            reduced.copy_(counters)
+            dist.all_reduce(reduced)
         t1.record(stream)
         return t0, t1
 
-    side = torch.cuda.Stream(dev) if world > 1 else None
-    done = torch.cuda.Event()
     reduced = torch.zeros_like(counters)
 
     def barrier():
@@ -350,8 +345,7 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(3, args.warmup)):
-        step()
+    timed(max(3, args.warmup))                         # warm-up steps (and NCCL's lazy communicator set-up)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
@@ -362,8 +356,6 @@ def run_gpu_arm(args):
     barrier()
     launches = gswm.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
-    if world > 1:
-        side.synchronize()
     n_steps_total = max(3, args.warmup) + args.steps
     torch.cuda.synchronize(dev)
     final = (reduced if world > 1 else counters).cpu().numpy().tolist()   # accumulated over every step so far
@@ -374,7 +366,7 @@ def run_gpu_arm(args):
     inst_steps = min(args.steps, 200)
     # the same step with both kernels on ONE stream (no co-scheduling), for reference
     barrier()
-    s_begin, s_end = timed(inst_steps, serial=True)
+    s_begin, s_end = timed(inst_steps, serial=True, reduce=False)
     barrier()
     serial_ms = s_begin.elapsed_time(s_end) / inst_steps
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
