@@ -294,6 +294,7 @@ def run_gpu_arm(args):
 
     # ---- resident inputs: key material on device, noisy latents for the extract side -------------------------
     from gswm.codec import _DeviceJob
+    from gswm.sharding import allreduce_counters
     import ctypes as C
     lib = gswm._lib.lib()
     dj = _DeviceJob(km, B, n, dev)
@@ -334,7 +335,7 @@ def run_gpu_arm(args):
         stream.wait_event(joined)
         if world > 1 and reduce:
             reduced.copy_(counters)
-            dist.all_reduce(reduced)
+            allreduce_counters(reduced)                # gswm/sharding.py: dist.all_reduce(SUM) over NCCL
         t1.record(stream)
         return t0, t1
 
