@@ -485,6 +485,16 @@ struct NegatedBits16 {
     return __byte_perm(nx, ny, 0x7531);                              // bytes: x.b1, x.b3, y.b1, y.b3
   }
 };
+// fp64 (what gs_insert.py:75 returns and a float64 caller hands to extract.py:83): the reference's own threshold, compared
+// in double.  Not a throughput path (fp64 compares run at 1/64 rate); it keeps float64 callers on the device.
+template <>
+struct NegatedBits<double> {
+  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g) {
+    const double2 a = reinterpret_cast<const double2*>(stage)[2 * g], b = reinterpret_cast<const double2*>(stage)[2 * g + 1];
+    const double t = -6.957291061679417e-17;                          // int(norm.cdf(z) * 2) == 1  <=>  z >= t
+    return (a.x < t ? 0x00000080u : 0u) | (a.y < t ? 0x00008000u : 0u) | (b.x < t ? 0x00800000u : 0u) | (b.y < t ? 0x80000000u : 0u);
+  }
+};
 template <>
 struct NegatedBits<__half> : NegatedBits16<__half2, 0x0000u> {};
 template <>
@@ -935,7 +945,7 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   int rc = check_job(job, true);
   if (rc) return rc;
   if (!d_z || !d_msg_out) return GSWM_E_NULL;
-  if (z_dtype != GSWM_F32 && z_dtype != GSWM_F16 && z_dtype != GSWM_BF16) return GSWM_E_DTYPE;
+  if (z_dtype != GSWM_F32 && z_dtype != GSWM_F16 && z_dtype != GSWM_BF16 && z_dtype != GSWM_F64) return GSWM_E_DTYPE;
   if (!aligned16(d_z) || (reinterpret_cast<uintptr_t>(d_msg_out) & 3u)) return GSWM_E_ALIGN;
   const int64_t copies = job->n_elems / job->msg_bits;
   if (d_counts && copies > 65535) return GSWM_E_RANGE;
@@ -953,7 +963,7 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
   a.copies = (uint32_t)copies;
   a.n_latents = job->n_latents;
-  const int64_t chunk_elems = z_dtype == GSWM_F32 ? Chunk<float>::kElems : Chunk<__half>::kElems;
+  const int64_t chunk_elems = z_dtype == GSWM_F32 ? Chunk<float>::kElems : z_dtype == GSWM_F64 ? Chunk<double>::kElems : Chunk<__half>::kElems;
   a.chunks_per_latent = (uint32_t)((job->n_elems + chunk_elems - 1) / chunk_elems);
   const bool pow2 = (1024 % job->msg_bits) == 0;
   a.ks_cache_tiles = (!job->per_latent && a.tiles_per_latent <= 8) ? a.tiles_per_latent : 0;
@@ -962,6 +972,7 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
   const size_t smem = (size_t)stages * kStageBytes +
                       (size_t)((a.ks_cache_tiles ? a.ks_cache_tiles : 1u) * kTileWords + job->msg_bits) * sizeof(uint32_t);
   if (z_dtype == GSWM_F32) rc = launch_extract<float>(a, job->per_latent != 0, pow2, smem, st);
+  else if (z_dtype == GSWM_F64) rc = launch_extract<double>(a, job->per_latent != 0, pow2, smem, st);
   else if (z_dtype == GSWM_F16) rc = launch_extract<__half>(a, job->per_latent != 0, pow2, smem, st);
   else rc = launch_extract<__nv_bfloat16>(a, job->per_latent != 0, pow2, smem, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -261,10 +261,10 @@ int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, i
   int rc = check_host_job(p, job, false);
   if (rc) return rc;
   if (!h_z || !h_msg_out) return GSWM_E_NULL;
-  if (z_dtype != GSWM_F32 && z_dtype != GSWM_F16 && z_dtype != GSWM_BF16) return GSWM_E_DTYPE;
+  if (z_dtype != GSWM_F32 && z_dtype != GSWM_F16 && z_dtype != GSWM_BF16 && z_dtype != GSWM_F64) return GSWM_E_DTYPE;
   if ((job->n_elems % job->msg_bits) != 0) return GSWM_E_MSGLEN;
   GSWM_CUDA(cudaSetDevice(p->device));
-  const size_t esz = z_dtype == GSWM_F32 ? 4 : 2;
+  const size_t esz = z_dtype == GSWM_F32 ? 4 : z_dtype == GSWM_F64 ? 8 : 2;
   const size_t z_row = (size_t)job->n_elems * esz;
   const int64_t mb = job->msg_bits / 8;
   const bool want_matched = h_matched && job->h_msgs;

@@ -240,10 +240,10 @@ class ExtractResult:
 
 def extract_batch(z: torch.Tensor, km: KeyMaterial, want_counts: bool = False,
                   counters: Optional[torch.Tensor] = None) -> ExtractResult:
-    """Decode a batch of inverted latents ``z`` [B, ...] (fp32 / fp16 / bf16, CUDA)."""
+    """Decode a batch of inverted latents ``z`` [B, ...] (fp32 / fp16 / bf16 / fp64, CUDA)."""
     if not z.is_cuda:
         raise ValueError("z must be a CUDA tensor (there is no CPU path)")
-    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
         raise ValueError(f"unsupported latent dtype {z.dtype}")
     dev = z.device
     z = z.contiguous()
@@ -365,8 +365,8 @@ class HostPipe:
         """Decode host latents [B, ...]; returns (messages u8 [B, L/8], counts u16 or None, matched i32 or None,
         counters i64[4]) as numpy arrays."""
         t = torch.from_numpy(z) if isinstance(z, np.ndarray) else z
-        if t.is_cuda or t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
-            raise ValueError("z must be a host fp32 / fp16 / bf16 array")
+        if t.is_cuda or t.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
+            raise ValueError("z must be a host fp32 / fp16 / bf16 / fp64 array")
         t = t.contiguous()
         b = t.shape[0]
         n = _n_elems(t.shape[1:])

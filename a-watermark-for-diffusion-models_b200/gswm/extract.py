@@ -40,11 +40,8 @@ def recover_exactracted_message(reversed_latents, args) -> str:
         raise ValueError("cannot convert float NaN to integer")
     if (z >= _CDF_ONE).any():
         raise ValueError("invalid literal for int() with base 2: cdf(z) * 2 == 2")
-    if z.dtype == torch.float64:
-        # keep the float64 threshold exact: quantise on the host side of the copy, ship +-1
-        z = torch.where(z >= _CDF_HALF, 1.0, -1.0).to(torch.float32)
-    elif z.dtype not in (torch.float32, torch.float16, torch.bfloat16):
-        z = z.to(torch.float32)
+    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
+        z = z.to(torch.float32)                     # integer tensors etc.; float64 is decoded as float64 on the device
     msg_bits = int(args.message_length)
     km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)
     if z.numel() % msg_bits:
@@ -83,7 +80,7 @@ def evaluate_latents(names, reversed_latents, args, result_file=None):
     (extracted bit strings, accuracies, average)."""
     z = _as_tensor(reversed_latents)
     z = z.reshape(z.shape[0], -1)
-    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
         z = z.to(torch.float32)
     msg_bits = int(args.message_length)
     km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)

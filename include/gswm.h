@@ -125,8 +125,9 @@ int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_la
 /*
  * Extract -- replaces extract.recover_exactracted_message (extract.py:72-101) and the counting half
  * of calculate_bit_accuracy (extract.py:103-110) for a batch of inverted latents d_z
- * [n_latents][n_elems] of type z_dtype (GSWM_F32 / GSWM_F16 / GSWM_BF16):
+ * [n_latents][n_elems] of type z_dtype (GSWM_F32 / GSWM_F16 / GSWM_BF16 / GSWM_F64):
  *   bit = int(norm.cdf(z)*2)  ==  (z >= -6.957291061679417e-17)       extract.py:82-84
+ *   (the threshold is applied in the input's own type: the smallest fp32 / bf16 value >= it, +0 for fp16, itself for fp64)
  *   decrypt with the keystream, count ones per message position over the n_elems/msg_bits copies,
  *   strict majority (tie -> 0)                                         extract.py:86-99
  * Outputs (each may be NULL except d_msg_out):

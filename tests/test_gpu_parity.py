@@ -201,7 +201,7 @@ def test_extract_golden_strings(gswm, cuda_device, golden, golden_arrays):
     base = golden_arrays["cli_lthero_z32"]
     msg = gswm.pad_message("lthero", 32)
     for c in golden["extract"]:
-        if "noise_seed" not in c or c["dtype"] == "float64":
+        if "noise_seed" not in c:
             continue
         z = _noisy(base, c["sigma"], c["noise_seed"], c["dtype"])
         km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
@@ -212,7 +212,7 @@ def test_extract_golden_strings(gswm, cuda_device, golden, golden_arrays):
         assert res.bit_accuracy() == c["bit_accuracy"]
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.float64])
 @pytest.mark.parametrize("shape,L", [((4, 64, 64), 256), ((4, 128, 128), 256), ((4, 64, 64), 32), ((4, 128, 128), 1024),
                                      ((4, 96, 64), 96), ((4, 8, 16), 512), ((4, 64, 64), 2048), ((4, 160, 128), 320),
                                      ((4, 8, 8), 32), ((4, 152, 104), 256), ((4, 72, 72), 64)])
@@ -225,7 +225,7 @@ def test_extract_counts_vs_oracle(gswm, cuda_device, dtype, shape, L):
     z = gswm.embed_batch(b, shape, km, 11, 0, 0, cuda_device)
     zn = (z + 1.7 * torch.from_numpy(rs.standard_normal((b, *shape))).to(cuda_device).float()).clamp(max=8.0).to(dtype)
     res = gswm.extract_batch(zn, km, want_counts=True)
-    zh = zn.float().cpu().numpy()
+    zh = zn.double().cpu().numpy() if dtype == torch.float64 else zn.float().cpu().numpy()
     matched_total = 0
     for i in range(b):
         counts = O.vote_counts(zh[i], KEY, NONCE, L)
@@ -270,6 +270,15 @@ def test_extract_quantiser_edges(gswm, cuda_device, golden):
     km = gswm.KeyMaterial.make(KEY, NONCE, None, 512)        # one copy: counts == decrypted bits
     res = gswm.extract_batch(torch.from_numpy(z).reshape(1, 4, 8, 16).to(cuda_device), km, want_counts=True)
     assert np.array_equal(res.counts[0].cpu().numpy().astype(np.uint32), O.vote_counts(z, KEY, NONCE, 512))
+    # float64 input is compared in float64 on the device: the reference's exact switch-over value and its neighbours
+    z64 = np.full(512, -1.0, dtype=np.float64)
+    v64 = [float(e["z"]) for e in golden["quantise_edges"] if np.isfinite(float(e["z"])) and float(e["z"]) < 8.0]
+    v64 += [O.CDF_HALF_THRESHOLD, np.nextafter(O.CDF_HALF_THRESHOLD, -1.0), np.nextafter(O.CDF_HALF_THRESHOLD, 1.0),
+            -6.957291061679417e-17, -6.957291061679418e-17, 5e-324, -5e-324, 1e-300, -1e-300, -7e-17, -6e-17]
+    z64[:len(v64)] = v64
+    assert np.array_equal(O.quantise(z64), (z64 >= O.CDF_HALF_THRESHOLD).astype(np.uint8))
+    res = gswm.extract_batch(torch.from_numpy(z64).reshape(1, 4, 8, 16).to(cuda_device), km, want_counts=True)
+    assert np.array_equal(res.counts[0].cpu().numpy().astype(np.uint32), O.vote_counts(z64, KEY, NONCE, 512))
     for dt in (torch.float16, torch.bfloat16):
         zz = torch.tensor([0.0, -0.0, 6e-8, -6e-8, 1.0, -1.0, 8.0, -65504.0] * 64, dtype=dt)
         # bit patterns the arithmetic cannot produce by rounding: smallest / largest subnormals of either sign
