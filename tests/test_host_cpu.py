@@ -65,6 +65,20 @@ def test_abi_basics_without_gpu(gswm):
     assert lib.gswm_chacha20_keystream(16, 16, 1, 100, 16, None) == -2
 
 
+def test_header_is_plain_c_and_links_from_c(gswm, tmp_path):
+    """include/gswm.h compiles as strict C99, libgswm.so links from a C program, and argument errors come back before any
+    CUDA call (tests/c_abi/abi_check.c runs without a GPU)."""
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(gswm._lib.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}",
+                         os.path.join(ROOT, "tests", "c_abi", "abi_check.c"), "-o", str(exe), f"-L{libdir}", "-lgswm",
+                         f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "abi_check ok" in run.stdout
+
+
 def test_uniform_source_rounds_match_oracle(gswm):
     # the oracle restates the library's uniform source; both must run the same number of Philox rounds
     assert gswm._lib.lib().gswm_philox_rounds() == O.GSWM_PHILOX_ROUNDS
