@@ -56,26 +56,43 @@ def gs_watermark_init_noise_batch(key_hex, nonce_hex, message, batch_size, width
 def common_ksampler(model, seed, steps, cfg, sampler_name, scheduler, positive, negative, latent, denoise=1.0,
                     disable_noise=False, start_step=None, last_step=None, force_full_denoise=False, use_GS=False,
                     GS_latent_noise=None):
-    """nodes.py:141-164 (ComfyUI sampler glue; the watermarked noise replaces prepare_noise when use_GS)."""
+    """Sampler glue with the reference's signature (nodes.py:141-164): the watermarked noise takes the place of
+    ``prepare_noise`` when ``use_GS`` is set; everything else is handed to ``comfy.sample.sample`` untouched."""
     import comfy.sample
     import comfy.utils
     import latent_preview
 
-    latent_image = latent["samples"]
+    x0 = latent["samples"]
     if use_GS:
-        noise = GS_latent_noise["samples"]
+        start_noise = GS_latent_noise["samples"]
     elif disable_noise:
-        noise = torch.zeros(latent_image.size(), dtype=latent_image.dtype, layout=latent_image.layout, device="cpu")
+        start_noise = torch.zeros_like(x0, device="cpu")
     else:
-        noise = comfy.sample.prepare_noise(latent_image, seed, latent.get("batch_index"))
-    callback = latent_preview.prepare_callback(model, steps)
-    samples = comfy.sample.sample(model, noise, steps, cfg, sampler_name, scheduler, positive, negative, latent_image,
-                                  denoise=denoise, disable_noise=disable_noise, start_step=start_step, last_step=last_step,
-                                  force_full_denoise=force_full_denoise, noise_mask=latent.get("noise_mask"),
-                                  callback=callback, disable_pbar=not comfy.utils.PROGRESS_BAR_ENABLED, seed=seed)
-    out = latent.copy()
-    out["samples"] = samples
-    return (out,)
+        start_noise = comfy.sample.prepare_noise(x0, seed, latent.get("batch_index"))
+    sampler_kwargs = dict(denoise=denoise, disable_noise=disable_noise, start_step=start_step, last_step=last_step,
+                          force_full_denoise=force_full_denoise, noise_mask=latent.get("noise_mask"),
+                          callback=latent_preview.prepare_callback(model, steps),
+                          disable_pbar=not comfy.utils.PROGRESS_BAR_ENABLED, seed=seed)
+    result = dict(latent)
+    result["samples"] = comfy.sample.sample(model, start_noise, steps, cfg, sampler_name, scheduler, positive, negative, x0,
+                                            **sampler_kwargs)
+    return (result,)
+
+
+# ---- node widgets, declared as compact tables (same names, order, defaults and ranges as nodes.py:170-186,213-223) ----
+def _int(default, lo, hi, step=None):
+    spec = {"default": default, "min": lo, "max": hi}
+    if step is not None:
+        spec["step"] = step
+    return ("INT", spec)
+
+
+def _sockets(*names_and_types):
+    return {name: (kind,) for name, kind in names_and_types}
+
+
+def _toggle(first, second):
+    return ([first, second],)
 
 
 def _sampler_choices():
@@ -87,71 +104,65 @@ def _sampler_choices():
 
 
 class GSKSamplerAdvanced:
-    """nodes.py:167-207."""
-
-    @classmethod
-    def INPUT_TYPES(s):
-        samplers, schedulers = _sampler_choices()
-        return {"required": {
-            "model": ("MODEL",),
-            "add_GS_noise": (["enable", "disable"],),
-            "add_noise": (["disable", "enable"],),
-            "noise_seed": ("INT", {"default": 42, "min": 0, "max": 0xffffffffffffffff}),
-            "steps": ("INT", {"default": 20, "min": 1, "max": 10000}),
-            "cfg": ("FLOAT", {"default": 8.0, "min": 0.0, "max": 100.0, "step": 0.1, "round": 0.01}),
-            "sampler_name": (samplers,),
-            "scheduler": (schedulers,),
-            "positive": ("CONDITIONING",),
-            "negative": ("CONDITIONING",),
-            "latent_image": ("LATENT",),
-            "GS_latent_noise": ("LATENT",),
-            "start_at_step": ("INT", {"default": 0, "min": 0, "max": 10000}),
-            "end_at_step": ("INT", {"default": 10000, "min": 0, "max": 10000}),
-            "return_with_leftover_noise": (["disable", "enable"],),
-        }}
+    """KSamplerAdvanced with a second LATENT input carrying the watermarked start noise (nodes.py:167-207)."""
 
     RETURN_TYPES = ("LATENT",)
     FUNCTION = "sample"
     CATEGORY = "GSWatermark-lthero/sampling"
 
+    @classmethod
+    def INPUT_TYPES(cls):
+        samplers, schedulers = _sampler_choices()
+        w = _sockets(("model", "MODEL"))
+        w["add_GS_noise"] = _toggle("enable", "disable")
+        w["add_noise"] = _toggle("disable", "enable")
+        w["noise_seed"] = _int(42, 0, 2 ** 64 - 1)
+        w["steps"] = _int(20, 1, 10000)
+        w["cfg"] = ("FLOAT", {"default": 8.0, "min": 0.0, "max": 100.0, "step": 0.1, "round": 0.01})
+        w["sampler_name"] = (samplers,)
+        w["scheduler"] = (schedulers,)
+        w.update(_sockets(("positive", "CONDITIONING"), ("negative", "CONDITIONING"), ("latent_image", "LATENT"),
+                          ("GS_latent_noise", "LATENT")))
+        w["start_at_step"] = _int(0, 0, 10000)
+        w["end_at_step"] = _int(10000, 0, 10000)
+        w["return_with_leftover_noise"] = _toggle("disable", "enable")
+        return {"required": w}
+
     def sample(self, model, add_GS_noise, add_noise, noise_seed, steps, cfg, sampler_name, scheduler, positive, negative,
                latent_image, GS_latent_noise, start_at_step, end_at_step, return_with_leftover_noise, denoise=1.0):
+        flags = dict(use_GS=add_GS_noise == "enable", disable_noise=add_noise == "disable",
+                     force_full_denoise=return_with_leftover_noise != "enable")
         return common_ksampler(model, noise_seed, steps, cfg, sampler_name, scheduler, positive, negative, latent_image,
-                               denoise=denoise, disable_noise=add_noise == "disable", start_step=start_at_step,
-                               last_step=end_at_step, force_full_denoise=return_with_leftover_noise != "enable",
-                               use_GS=add_GS_noise == "enable", GS_latent_noise=GS_latent_noise)
+                               denoise=denoise, start_step=start_at_step, last_step=end_at_step,
+                               GS_latent_noise=GS_latent_noise, **flags)
 
 
 class GSLatent:
-    """nodes.py:210-240."""
-
-    @classmethod
-    def INPUT_TYPES(s):
-        return {"required": {
-            "use_seed": ("INT", {"default": 1, "min": 0, "max": 1}),
-            "seed": ("INT", {"default": 42, "min": 0, "max": 0xffffffff}),
-            "width": ("INT", {"default": 512, "min": 64, "max": MAX_RESOLUTION, "step": 8}),
-            "height": ("INT", {"default": 512, "min": 64, "max": MAX_RESOLUTION, "step": 8}),
-            "key": ("STRING", {"default": codec.DEFAULT_KEY_HEX}),
-            "nonce": ("STRING", {"default": codec.DEFAULT_NONCE_HEX}),
-            "message": ("STRING", {"default": "lthero"}),
-            "message_length": ("INT", {"default": -1, "min": 32, "max": 1024, "step": 32}),
-            "batch_size": ("INT", {"default": 1, "min": 1, "max": 64}),
-        }}
+    """Builds the watermarked LATENT batch on the GPU (nodes.py:210-240)."""
 
     RETURN_TYPES = ("LATENT", "IMAGE")
     FUNCTION = "create_gs_latents"
     CATEGORY = "GSWatermark-lthero/latent/noise"
 
+    @classmethod
+    def INPUT_TYPES(cls):
+        text = {"key": codec.DEFAULT_KEY_HEX, "nonce": codec.DEFAULT_NONCE_HEX, "message": "lthero"}
+        w = {"use_seed": _int(1, 0, 1), "seed": _int(42, 0, 2 ** 32 - 1), "width": _int(512, 64, MAX_RESOLUTION, 8), "height": _int(512, 64, MAX_RESOLUTION, 8)}
+        w.update({name: ("STRING", {"default": value}) for name, value in text.items()})
+        w["message_length"] = _int(-1, 32, 1024, 32)
+        w["batch_size"] = _int(1, 1, 64)
+        return {"required": w}
+
     def create_gs_latents(self, key, nonce, message, batch_size, use_seed, seed, width, height, message_length):
         if use_seed == 1:
-            # one seeded latent replicated batch_size times (nodes.py:232-235)
+            # the reference embeds ONE seeded latent and replicates it batch_size times (nodes.py:232-235)
             one = gs_watermark_init_noise(key, nonce, "cpu", message, use_seed, seed, width=width, height=height,
                                           message_length=message_length)
-            latent = torch.stack([one for _ in range(batch_size)]).float()
+            batch = one.float().unsqueeze(0).repeat(batch_size, 1, 1, 1)
         else:
-            latent = gs_watermark_init_noise_batch(key, nonce, message, batch_size, width, height, message_length).float()
-        return ({"samples": latent}, latent[0])
+            # batch_size independent latents (nodes.py:237): one launch instead of batch_size calls
+            batch = gs_watermark_init_noise_batch(key, nonce, message, batch_size, width, height, message_length).float()
+        return ({"samples": batch}, batch[0])
 
 
 NODE_CLASS_MAPPINGS = {"Lthero_GSLatent": GSLatent, "Lthero_GS_KSamplerAdvanced": GSKSamplerAdvanced}

@@ -203,3 +203,66 @@ def test_shard_range(gswm):
             assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in rs]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_comfy_nodes_interface_without_comfyui(gswm, monkeypatch):
+    """Widget declarations and sampler glue of the ComfyUI drop-in (nodes.py:141-252), against stub comfy modules:
+    names, order, defaults and ranges are what the reference declares; the GS latent replaces the start noise."""
+    import sys
+    import types
+
+    import torch
+
+    from gswm import comfy_nodes as cn
+
+    lat = cn.GSLatent.INPUT_TYPES()["required"]
+    assert list(lat) == ["use_seed", "seed", "width", "height", "key", "nonce", "message", "message_length", "batch_size"]
+    assert lat["seed"] == ("INT", {"default": 42, "min": 0, "max": 0xffffffff})
+    assert lat["width"] == lat["height"] == ("INT", {"default": 512, "min": 64, "max": 8192, "step": 8})
+    assert lat["width"][1] is not lat["height"][1]
+    assert lat["key"] == ("STRING", {"default": gswm.DEFAULT_KEY_HEX}) and lat["message"] == ("STRING", {"default": "lthero"})
+    assert lat["message_length"] == ("INT", {"default": -1, "min": 32, "max": 1024, "step": 32})
+    assert lat["batch_size"] == ("INT", {"default": 1, "min": 1, "max": 64})
+    ks = cn.GSKSamplerAdvanced.INPUT_TYPES()["required"]
+    assert list(ks) == ["model", "add_GS_noise", "add_noise", "noise_seed", "steps", "cfg", "sampler_name", "scheduler",
+                        "positive", "negative", "latent_image", "GS_latent_noise", "start_at_step", "end_at_step",
+                        "return_with_leftover_noise"]
+    assert ks["add_GS_noise"] == (["enable", "disable"],) and ks["add_noise"] == (["disable", "enable"],)
+    assert ks["noise_seed"] == ("INT", {"default": 42, "min": 0, "max": 0xffffffffffffffff})
+    assert ks["cfg"] == ("FLOAT", {"default": 8.0, "min": 0.0, "max": 100.0, "step": 0.1, "round": 0.01})
+    assert ks["GS_latent_noise"] == ("LATENT",) and ks["end_at_step"] == ("INT", {"default": 10000, "min": 0, "max": 10000})
+    assert cn.GSLatent.RETURN_TYPES == ("LATENT", "IMAGE") and cn.GSLatent.FUNCTION == "create_gs_latents"
+    assert cn.GSKSamplerAdvanced.RETURN_TYPES == ("LATENT",) and cn.GSKSamplerAdvanced.FUNCTION == "sample"
+
+    calls = {}
+
+    def fake_sample(model, noise, steps, cfg, sampler_name, scheduler, positive, negative, latent_image, **kw):
+        calls["noise"], calls["kw"], calls["latent_image"] = noise, kw, latent_image
+        return noise + 1
+
+    comfy = types.ModuleType("comfy")
+    comfy.sample = types.ModuleType("comfy.sample")
+    comfy.sample.sample = fake_sample
+    comfy.sample.prepare_noise = lambda latent_image, seed, inds: torch.full_like(latent_image, float(seed))
+    comfy.utils = types.ModuleType("comfy.utils")
+    comfy.utils.PROGRESS_BAR_ENABLED = True
+    lp = types.ModuleType("latent_preview")
+    lp.prepare_callback = lambda model, steps: ("cb", steps)
+    for name, mod in (("comfy", comfy), ("comfy.sample", comfy.sample), ("comfy.utils", comfy.utils), ("latent_preview", lp)):
+        monkeypatch.setitem(sys.modules, name, mod)
+
+    empty = {"samples": torch.zeros(2, 4, 8, 8), "noise_mask": "mask"}
+    gs = {"samples": torch.ones(2, 4, 8, 8)}
+    node = cn.GSKSamplerAdvanced()
+    (out,) = node.sample("m", "enable", "enable", 7, 20, 8.0, "euler", "normal", "p", "n", empty, gs, 0, 10000, "disable")
+    assert torch.equal(calls["noise"], gs["samples"]) and torch.equal(out["samples"], gs["samples"] + 1)
+    assert out["noise_mask"] == "mask" and out is not empty and torch.equal(empty["samples"], torch.zeros(2, 4, 8, 8))
+    kw = calls["kw"]
+    assert kw["force_full_denoise"] is True and kw["disable_noise"] is False and kw["noise_mask"] == "mask"
+    assert kw["callback"] == ("cb", 20) and kw["disable_pbar"] is False and kw["seed"] == 7
+    assert kw["start_step"] == 0 and kw["last_step"] == 10000 and kw["denoise"] == 1.0
+    node.sample("m", "disable", "enable", 7, 20, 8.0, "euler", "normal", "p", "n", empty, gs, 0, 10000, "enable")
+    assert torch.equal(calls["noise"], torch.full((2, 4, 8, 8), 7.0)) and calls["kw"]["force_full_denoise"] is False
+    node.sample("m", "disable", "disable", 7, 20, 8.0, "euler", "normal", "p", "n", empty, gs, 0, 10000, "enable")
+    assert torch.equal(calls["noise"], torch.zeros(2, 4, 8, 8)) and calls["noise"].device.type == "cpu"
+    assert calls["kw"]["disable_noise"] is True
