@@ -266,3 +266,56 @@ def test_comfy_nodes_interface_without_comfyui(gswm, monkeypatch):
     node.sample("m", "disable", "disable", 7, 20, 8.0, "euler", "normal", "p", "n", empty, gs, 0, 10000, "enable")
     assert torch.equal(calls["noise"], torch.zeros(2, 4, 8, 8)) and calls["noise"].device.type == "cpu"
     assert calls["kw"]["disable_noise"] is True
+
+
+def test_webui_scripts_patch_and_restore_with_stub_webui(gswm, monkeypatch):
+    """Script.run of both webui drop-ins against stub ``modules`` / ``gradio``: the hook is in place while
+    process_images runs (v1.5.2:123-138, v1.6.0:175-190), the UI fields land in the shared globals, and the original
+    hook is back afterwards -- also when process_images raises (the reference's v1.6.0 never restores it)."""
+    import sys
+    import types
+
+    from gswm import webui_v152 as w5
+    from gswm import webui_v160 as w6
+
+    seen = {}
+    processing = types.ModuleType("modules.processing")
+    processing.create_random_tensors = original_creator = lambda *a, **k: "stock tensors"
+    rng = types.ModuleType("modules.rng")
+    rng.ImageRNG = original_rng = type("ImageRNG", (), {})
+
+    def process_images(p):
+        seen["creator"], seen["rng"] = processing.create_random_tensors, rng.ImageRNG
+        seen["globals"] = (w5.global_message, w5.global_key, w5.global_nonce, w5.global_randomSeed,
+                           w5.global_use_randomSeed, w5.global_use_repeat)
+        if p == "boom":
+            raise RuntimeError("sampler failed")
+        return "processed"
+
+    processing.process_images = process_images
+    scripts = types.ModuleType("modules.scripts")
+    scripts.Script = type("Script", (), {})
+    modules = types.ModuleType("modules")
+    modules.processing, modules.scripts, modules.rng = processing, scripts, rng
+    gradio = types.ModuleType("gradio")
+    for name, mod in (("modules", modules), ("modules.processing", processing), ("modules.scripts", scripts),
+                      ("modules.rng", rng), ("gradio", gradio)):
+        monkeypatch.setitem(sys.modules, name, mod)
+
+    s5 = w5._make_script()()
+    assert s5.title() == "GS_watermark_insert"
+    assert s5.run("p", "msg", "aa" * 32, "bb" * 16, "1234", "1", "0") == "processed"
+    assert seen["creator"] is w5.advanced_creator and processing.create_random_tensors is original_creator
+    assert seen["globals"] == ("msg", "aa" * 32, "bb" * 16, 1234, 1, 0)
+    with pytest.raises(RuntimeError):
+        s5.run("boom", "m", "k", "n", "5", "0", "1")
+    assert processing.create_random_tensors is original_creator and seen["globals"][3:] == (5, 0, 1)
+
+    s6 = w6._make_script()()
+    assert s6.run("p", "other", "cc" * 32, "", "77", "0", "1") == "processed"
+    assert seen["rng"] is w6.modified_ImageRNG and rng.ImageRNG is original_rng
+    assert seen["globals"] == ("other", "cc" * 32, "", 77, 0, 1)
+    assert (w6.global_message, w6.global_randomSeed) == ("other", 77)        # one shared state for both generations
+    with pytest.raises(RuntimeError):
+        s6.run("boom", "m", "k", "n", "5", "0", "0")
+    assert rng.ImageRNG is original_rng
