@@ -276,6 +276,10 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        gswm.build()                                  # no-op when libgswm.so is up to date; there is no fallback path
+    if world > 1:
+        dist.barrier()
     gswm._lib.lib()
 
     shape = SHAPES[args.shape]

@@ -24,7 +24,8 @@ NONCE = bytes.fromhex(O.DEFAULT_NONCE_HEX)
 @pytest.fixture(scope="module")
 def gswm(cuda_device):
     import gswm as g
-    g._lib.lib()   # raises if the extension is missing: no fallback
+    g.build()      # no-op when libgswm.so is up to date (it travels with the tree); compiles it with nvcc otherwise
+    g._lib.lib()   # raises if the extension cannot be loaded: there is no fallback path
     return g
 
 
