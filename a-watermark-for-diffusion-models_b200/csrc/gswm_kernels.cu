@@ -219,8 +219,17 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
 #else
   auto emit = [&](uint32_t i, const uint32_t (&f)[4]) {
     if (kGuard && i >= n_f4) return;
+#ifdef GSWM_WHATIF_NOSIGN
+    const float4 sgn = make_float4(1.f, 1.f, 1.f, 1.f);                // diagnostic build: no bucket bits, no LUT (gswm_math.cuh)
+#else
     const float4 sgn = my_sign[2u * s_bytes[i >> 1]];
-    __stcs(out4 + i, bucket_quantile4_f32(f[0], f[1], f[2], f[3], sgn));
+#endif
+#ifdef GSWM_WHATIF_NOSTORE
+    const float4 zq = bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn);
+    if (zq.x == 123.456f) __stcs(out4 + i, zq);                        // diagnostic build: arithmetic kept alive, nothing written
+#else
+    __stcs(out4 + i, bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn));   // !kGuard: every lane of the warp is here
+#endif
   };
   emit(i0, f0);
   emit(i0 + kThreads, f1);

@@ -14,7 +14,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 _INCLUDE = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include")
-LIB_PATH = os.path.join(_HERE, "libgswm.so")
+# GSWM_LIB: load another build of the same ABI instead (A/B runs of kernel variants through bench.py / the tests)
+LIB_PATH = os.environ.get("GSWM_LIB") or os.path.join(_HERE, "libgswm.so")
 SOURCES = ["gswm_kernels.cu", "gswm_pipe.cu"]
 
 GSWM_F32, GSWM_F16, GSWM_BF16, GSWM_F64 = 0, 1, 2, 3
@@ -48,6 +49,8 @@ def nvcc_command(out: str = LIB_PATH, extra=()):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libgswm.so for sm_100a (cross-compiles without a GPU).  Returns its path."""
+    if os.environ.get("GSWM_LIB"):          # an explicitly chosen build is never rebuilt or overwritten
+        return LIB_PATH
     srcs = [os.path.join(_CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".inc"))]
     deps.append(os.path.join(_INCLUDE, "gswm.h"))

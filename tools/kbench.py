@@ -68,7 +68,10 @@ def main():
         torch.cuda.synchronize()
         zn.copy_(z + 0.325 * torch.randn_like(z))
         res = {"lib": os.path.basename(path), "per_latent": per, "zdtype": str(zdt), "B": B, "n": n}
-        for name, fn in (("embed_us", embed), ("extract_us", extract), ("pair_us", lambda: (embed(), extract()))):
+        legs = (("embed_us", embed), ("extract_us", extract), ("pair_us", lambda: (embed(), extract())))
+        if os.environ.get("KB_ONLY_EMBED"):                     # tools/whatif.sh: diagnostic builds, embed timing only
+            legs = legs[:1]
+        for name, fn in legs:
             for _ in range(5):
                 fn()
             torch.cuda.synchronize()
@@ -82,13 +85,14 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
             res[name] = round(best, 2)
-        counters.zero_()
-        extract()
-        torch.cuda.synchronize()
-        res["exact"] = counters.cpu().tolist()
         bytes_ = B * n * 4
         res["embed_GBps"] = round(bytes_ / res["embed_us"] / 1e3, 1)
-        res["extract_GBps"] = round(B * n * zn.element_size() / res["extract_us"] / 1e3, 1)
+        if "extract_us" in res:
+            counters.zero_()
+            extract()
+            torch.cuda.synchronize()
+            res["exact"] = counters.cpu().tolist()
+            res["extract_GBps"] = round(B * n * zn.element_size() / res["extract_us"] / 1e3, 1)
         print(json.dumps(res), flush=True)
 
 
