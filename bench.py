@@ -374,19 +374,29 @@ def run_gpu_arm(args):
     s_begin, s_end = timed(inst_steps, serial=True, reduce=False)
     barrier()
     serial_ms = s_begin.elapsed_time(s_end) / inst_steps
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    barrier()
-    ev[0].record(stream)
-    for k in range(inst_steps):
+    # three bursts per kernel, each between one event pair; `ms` is the best burst (min and median), the
+    # median is reported next to it
+    def burst(launch):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(inst_steps):
+            launch()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) / inst_steps
+
+    def launch_embed():
         gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
-    ev[1].record(stream)
-    for k in range(inst_steps):
+
+    def launch_extract():
         gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
                                          counters.data_ptr(), ws2p, sp), "gswm_extract")
-    ev[2].record(stream)
-    barrier()
-    embed_ms = ev[0].elapsed_time(ev[1]) / inst_steps
-    extract_ms = ev[1].elapsed_time(ev[2]) / inst_steps
+
+    embed_bursts = sorted(burst(launch_embed) for _ in range(3))
+    extract_bursts = sorted(burst(launch_extract) for _ in range(3))
+    embed_ms, extract_ms = embed_bursts[0], extract_bursts[0]
+    embed_med, extract_med = embed_bursts[1], extract_bursts[1]
     clocks = sampler.stop() if rank == 0 else None
     tm = torch.tensor([total_ms, embed_ms, extract_ms, serial_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -448,8 +458,8 @@ def run_gpu_arm(args):
 
     peak, peak_src = measured_peak_gbs()
     lat_bytes = B * n * 4
-    k_embed = {"ms": embed_ms, "GBps": lat_bytes / (embed_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
-    k_extract = {"ms": extract_ms, "GBps": lat_bytes / (extract_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
+    k_embed = {"ms": embed_ms, "ms_median": embed_med, "GBps": lat_bytes / (embed_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
+    k_extract = {"ms": extract_ms, "ms_median": extract_med, "GBps": lat_bytes / (extract_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
     dom_name, dom = ("embed_kernel", k_embed) if embed_ms >= extract_ms else ("extract_kernel", k_extract)
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": dom["GBps"] / peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
@@ -476,7 +486,7 @@ def run_gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": workload_name(args), "latents_per_gpu": B, "latent_shape": [c, h, w], "msg_bits": L,
                    "l2": "inputs larger than L2 (2 x 268 MB streamed per step vs 126 MB L2)" if lat_bytes > 126e6 else
-                         "WARNING: working set fits L2", "timing": "CUDA events on the launch stream (the extract stream is forked after the start event and joined before the end event), max over ranks; per-kernel durations from %d back-to-back launches of each kernel between one event pair" % inst_steps,
+                         "WARNING: working set fits L2", "timing": "CUDA events on the launch stream (the extract stream is forked after the start event and joined before the end event), max over ranks; per-kernel durations: best (ms) and median (ms_median) of 3 bursts of %d back-to-back launches, each burst between one event pair" % inst_steps,
                    "schedule": "embed and extract of a step run on two CUDA streams and share the SMs (FMA-bound embed next to HBM-bound extract); roofline.step.serial_ms is the same step on one stream",
                    "uniform_source": "Philox4x32-%d, 23 bits per element" % lib.gswm_philox_rounds(),
                    "decode_exact": bool(exact), "counters": final},
