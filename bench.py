@@ -243,7 +243,7 @@ def ncu_pipe_summary(kernel):
     """Issue / pipe utilisation of `kernel` from the committed ncu --set full capture (profiles/), for the roofline block:
     the embed kernel is bound by the FMA pipes, not by HBM, and these are the numbers that say so."""
     try:
-        with open(os.path.join(ROOT, "profiles", f"r01c_{kernel.split('_')[0]}_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", f"r01h_{kernel.split('_')[0]}_ncu_summary.json")) as f:
             k = json.load(f)["kernels"][0]
         pick = {"issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
                 "fma_heavy_pipe_pct": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
@@ -251,7 +251,7 @@ def ncu_pipe_summary(kernel):
                 "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
                 "duration_us_under_ncu": "gpu__time_duration.sum"}
         out = {a: round(float(k[b]["value"]), 2) for a, b in pick.items()}
-        out["source"] = f"profiles/r01c_{kernel.split('_')[0]}_ncu_summary.json (cold, serialised launch)"
+        out["source"] = f"profiles/r01h_{kernel.split('_')[0]}_ncu_summary.json (cold, serialised launch)"
         return out
     except Exception:  # noqa: BLE001
         return None
