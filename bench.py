@@ -155,7 +155,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -170,16 +170,32 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def wait_ready(self, timeout=5.0):
+        """nvidia-smi takes a few hundred ms to print its first line: block until it is streaming, so that the timed
+        region (tens of ms) is sampled from its first millisecond."""
+        t0 = time.perf_counter()
+        while self.proc is not None and time.perf_counter() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.02)
+        return False
+
+    def stop(self, window=None):
+        """Median SM clock / throttle reasons over the samples whose timestamp lies inside `window` (datetime pair: the
+        timed region and the per-kernel bursts after it); all samples if none falls inside."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
+        import datetime as dt
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for ln in open(self.path):
@@ -187,21 +203,23 @@ class ClockSampler:
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                    ts = dt.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((ts, float(f[1]), float(f[2]), float(f[3]), [nm for nm, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for nm, v in zip(names, f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
         finally:
             try:
                 os.unlink(self.path)
             except OSError:
                 pass
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+        inside = [r for r in rows if window and window[0] <= r[0] <= window[1]]
+        use = inside or rows
+        return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)),
+                "reasons": sorted({nm for r in use for nm in r[4]}), "samples": len(use), "samples_total": len(rows),
+                "window": "timed region + per-kernel bursts" if inside else "whole run (no sample fell inside the timed window)",
+                "power_w_max": max(r[3] for r in use)}
 
 
 def measured_peak_gbs():
@@ -281,6 +299,9 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
     gswm._lib.lib()
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
+        sampler.start()                               # started early: it needs a few hundred ms before its first line
 
     shape = SHAPES[args.shape]
     n = int(np.prod(shape))
@@ -352,10 +373,11 @@ def run_gpu_arm(args):
 
     timed(max(3, args.warmup))                         # warm-up steps (and NCCL's lazy communicator set-up)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
-        sampler.start()
+    import datetime as _dt
+    if rank == 0:
+        sampler.wait_ready()
     launches0 = gswm.launch_count()
+    load_begin = _dt.datetime.now()
     barrier()
     t_begin, t_end = timed(args.steps)
     barrier()
@@ -397,7 +419,7 @@ def run_gpu_arm(args):
     extract_bursts = sorted(burst(launch_extract) for _ in range(3))
     embed_ms, extract_ms = embed_bursts[0], extract_bursts[0]
     embed_med, extract_med = embed_bursts[1], extract_bursts[1]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((load_begin, _dt.datetime.now())) if rank == 0 else None
     tm = torch.tensor([total_ms, embed_ms, extract_ms, serial_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
