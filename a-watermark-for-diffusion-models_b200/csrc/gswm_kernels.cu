@@ -182,10 +182,13 @@ __device__ __forceinline__ void build_sign_lut(float4* lut) {
 #endif
 // One SUPER-ITERATION of a tile: 1024 float4 = 4 per thread, fed by three Philox calls.
 // Philox counter word 0..1: G = ((global_latent * tiles + tile) * 4 + sidx) * 256 + tid; words 2..3: offset, call index.
-template <bool kGuard>
+// kHoisted (shared key, whole tile): the bucket nibbles of this thread's four float4 never change from latent to latent, so
+// the caller passes them pre-scaled (nibble << 4 in byte k of `sign_pack`) and `my_sign` is the 16-entry nibble table:
+// one PRMT + one LDS.128 per float4 instead of LDS.U8 + LEA + LDS.128 from the 8 KB byte table.
+template <bool kGuard, bool kHoisted = false>
 __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const uint8_t* __restrict__ s_bytes,
                                                       const float4* __restrict__ my_sign, float4* __restrict__ out4,
-                                                      uint64_t g_tile, uint32_t sidx, uint32_t n_f4) {
+                                                      uint64_t g_tile, uint32_t sidx, uint32_t n_f4, uint32_t sign_pack = 0) {
   const uint64_t g = g_tile + (uint64_t)sidx * kThreads;
   const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
 #if GSWM_PHILOX_CONST_KEYS
@@ -217,12 +220,14 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
   emit2(i0, i0 + kThreads, f0, f1);
   emit2(i0 + 2 * kThreads, i0 + 3 * kThreads, f2, f3);
 #else
-  auto emit = [&](uint32_t i, const uint32_t (&f)[4]) {
+  auto emit = [&](uint32_t i, const uint32_t (&f)[4], uint32_t k) {
     if (kGuard && i >= n_f4) return;
 #ifdef GSWM_WHATIF_NOSIGN
     const float4 sgn = make_float4(1.f, 1.f, 1.f, 1.f);                // diagnostic build: no bucket bits, no LUT (gswm_math.cuh)
 #else
-    const float4 sgn = my_sign[2u * s_bytes[i >> 1]];
+    const float4 sgn = kHoisted ? *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(my_sign) +
+                                                                    __byte_perm(sign_pack, 0u, 0x4440u | k))
+                                : my_sign[2u * s_bytes[i >> 1]];
 #endif
 #ifdef GSWM_WHATIF_NOSTORE
     const float4 zq = bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn);
@@ -231,10 +236,10 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
     __stcs(out4 + i, bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn));   // !kGuard: every lane of the warp is here
 #endif
   };
-  emit(i0, f0);
-  emit(i0 + kThreads, f1);
-  emit(i0 + 2 * kThreads, f2);
-  emit(i0 + 3 * kThreads, f3);
+  emit(i0, f0, 0);
+  emit(i0 + kThreads, f1, 1);
+  emit(i0 + 2 * kThreads, f2, 2);
+  emit(i0 + 3 * kThreads, f3, 3);
 #endif
 }
 
@@ -278,6 +283,7 @@ __global__ void __launch_bounds__(kThreads, kPerLatent ? GSWM_EMBED_MINB_PER_LAT
 embed_kernel(const EmbedArgs a) {
   __shared__ __align__(16) uint32_t s_ks[kTileWords];
   __shared__ __align__(16) float4 s_sign[512];
+  __shared__ __align__(16) float4 s_sign16[16];                       // nibble -> +-1.0f x4 (shared-key whole-tile path)
   const uint32_t tile = kPerLatent ? blockIdx.y : blockIdx.y >> 1;
   const uint32_t tiles = a.tiles_per_latent;
   const uint32_t words = tile_words(a.n_elems, tile);
@@ -285,6 +291,10 @@ embed_kernel(const EmbedArgs a) {
   trace_mark(0);
   griddep_launch_dependents();
   build_sign_lut(s_sign);
+  if (threadIdx.x < 16) {
+    const uint32_t n = threadIdx.x;
+    s_sign16[n] = make_float4((n & 8u) ? 1.f : -1.f, (n & 4u) ? 1.f : -1.f, (n & 2u) ? 1.f : -1.f, (n & 1u) ? 1.f : -1.f);
+  }
   if constexpr (!kPerLatent) {
     // Shared key: this CTA's half tile needs 16 ChaCha20 blocks, once.  Half a warp computes them here, AHEAD of the
     // grid dependency wait -- key material is final before the call is enqueued (gswm.h) -- so when the previous kernel
@@ -313,9 +323,19 @@ embed_kernel(const EmbedArgs a) {
     // -- tools/embed_trace.py -- but same-address atomics under this kernel's store traffic complete only every ~34 ns,
     // far too slow for one grab per latent: 67.6 us against 56.1 us.)
     if (n_f4 == kTileF4) {
+      // this thread's eight bucket nibbles (float4 (4 sidx + k) 256 + tid, sidx in {s0, s0 + 1}) are the same for every
+      // latent: fetched once, kept as table offsets (nibble << 4) in the bytes of two registers
+      uint32_t pack[2] = {0u, 0u};
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j) {
+        const uint32_t i = (4u * (s0 + (j >> 2)) + (j & 3u)) * kThreads + threadIdx.x;
+        const uint32_t byte = s_bytes[i >> 1];
+        const uint32_t nib = (threadIdx.x & 1u) ? (byte & 0xFu) : (byte >> 4);
+        pack[j >> 2] |= (nib << 4) << (8u * (j & 3u));
+      }
       for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
-        embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4);
-        embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4);
+        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0, n_f4, pack[0]);
+        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0 + 1, n_f4, pack[1]);
       }
     } else {
       for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
