@@ -319,3 +319,39 @@ def test_webui_scripts_patch_and_restore_with_stub_webui(gswm, monkeypatch):
     with pytest.raises(RuntimeError):
         s6.run("boom", "m", "k", "n", "5", "0", "0")
     assert rng.ImageRNG is original_rng
+
+
+def test_bench_clock_sampler_selects_samples_inside_the_timed_window():
+    """bench.py's nvidia-smi sampler: lines are parsed by timestamp, only those inside the timed window count (all of them
+    if none falls inside), throttle reasons are collected from the selected lines."""
+    import datetime as dt
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Done:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    def sampler_with(lines):
+        s = bench.ClockSampler(0)
+        with open(s.path, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        s.proc = Done()
+        return s
+
+    lines = ["2026/10/17 12:00:00.000, 1965, 1965, 200.0, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+             "2026/10/17 12:00:00.020, 1900, 1965, 900.5, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+             "2026/10/17 12:00:00.040, 1700, 1965, 1001.0, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+             "garbage line",
+             "2026/10/17 12:00:00.060, 1965, 1965, 150.0, 0x0000000000000000, Not Active, Active, Not Active, Not Active"]
+    t = lambda ms: dt.datetime(2026, 10, 17, 12, 0, 0, ms * 1000)
+    got = sampler_with(lines).stop((t(10), t(50)))
+    assert got["samples"] == 2 and got["samples_total"] == 4 and got["sm_mhz"] == 1800.0 and got["sm_max_mhz"] == 1965.0
+    assert got["reasons"] == ["sw_power_cap"] and got["power_w_max"] == 1001.0 and got["window"].startswith("timed region")
+    got = sampler_with(lines).stop((t(100), t(200)))                     # nothing inside: every sample is used, and says so
+    assert got["samples"] == 4 and got["window"].startswith("whole run") and got["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+    assert sampler_with(["garbage"]).stop(None)["reasons"] == ["no samples"]
+    s = bench.ClockSampler(0)
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"] and s.wait_ready(0.01) is False
