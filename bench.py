@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
+    ap.add_argument("--ref-step-seconds", type=float, default=None, help="--impl reference: CPU seconds per step (default: sized so the run ends within ~2 minutes)")
     return ap.parse_args()
 
 
@@ -122,7 +123,7 @@ def run_reference_arm(args):
     cores = len(os.sched_getaffinity(0))
     per_pair = calibrate_cpu(n, args.msg_bits)
     # each step: a bounded sample so that warmup + steps stays within ~2 minutes
-    budget_per_step = min(6.0, 100.0 / max(1, args.steps + args.warmup))
+    budget_per_step = args.ref_step_seconds or min(6.0, 100.0 / max(1, args.steps + args.warmup))
     ppw = max(2, int(budget_per_step / per_pair))
     pool = cpu_pool(cores)
     for _ in range(args.warmup):
