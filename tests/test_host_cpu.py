@@ -376,3 +376,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1"],
                            capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_bench_gpu_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback anywhere: without a CUDA device the product arm of bench.py exits non-zero and prints no JSON."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+    assert not any(ln.lstrip().startswith("{") for ln in out.stdout.splitlines())
