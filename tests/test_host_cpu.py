@@ -387,3 +387,21 @@ def test_bench_gpu_arm_refuses_to_run_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
     assert not any(ln.lstrip().startswith("{") for ln in out.stdout.splitlines())
+
+
+def test_kernel_coefficients_are_what_the_fit_tool_derives(tmp_path):
+    """csrc/gswm_coeffs.inc is generated, not transcribed: tools/fit_halfnormal_quantile.py with the parameters recorded in
+    the file's header reproduces it byte for byte, and reports an emulated-fp32 error inside the 1e-6 tolerance."""
+    inc = os.path.join(ROOT, "a-watermark-for-diffusion-models_b200", "csrc", "gswm_coeffs.inc")
+    header = open(inc).read().splitlines()[1]
+    m = re.match(r"// deg_central=(\d+) deg_tail=(\d+) w_split=([\d.]+)", header)
+    assert m, header
+    deg64 = len(re.search(r"#define GSWM_HNQ64_CENTRAL_COEFFS (.*)", open(inc).read()).group(1).split(",")) - 1
+    out = tmp_path / "coeffs.inc"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fit_halfnormal_quantile.py"), "--deg-central", m.group(1),
+                          "--deg-tail", m.group(2), "--w-split", m.group(3), "--deg64", str(deg64), "--out", str(out)],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert out.read_text() == open(inc).read()
+    errs = [float(x) for x in re.search(r"max rel err central ([\d.e+-]+)\s+tail ([\d.e+-]+)", res.stdout).groups()]
+    assert max(errs) < 6e-7

@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--w-split", type=float, default=5.0, help="central/tail split in w = -ln(1-v^2)")
     ap.add_argument("--deg64", type=int, default=16, help="degree of the float64-path polynomials")
     ap.add_argument("--no-write", action="store_true")
+    ap.add_argument("--out", default=OUT, help="where to write the coefficient header (default: csrc/gswm_coeffs.inc)")
     ap.add_argument("--exhaustive", action="store_true", help="evaluate all 2^23 inputs (slow-ish)")
     args = ap.parse_args()
 
@@ -215,7 +216,7 @@ def main():
     print(f"float64 path (deg {args.deg64}): fit error central {e64c:.3e}  tailA {e64a:.3e}  tailB {e64b:.3e}")
 
     if not args.no_write:
-        with open(OUT, "w") as fo:
+        with open(args.out, "w") as fo:
             fo.write("// Generated by tools/fit_halfnormal_quantile.py -- do not edit by hand.\n")
             fo.write(f"// deg_central={args.deg_central} deg_tail={args.deg_tail} w_split={args.w_split}\n")
             fo.write(f"#define GSWM_HNQ_KSCALE {2.0 ** c_shift!r}f\n")
@@ -231,7 +232,7 @@ def main():
             fo.write("#define GSWM_HNQ64_CENTRAL_COEFFS " + ", ".join(f"{float(c)!r}" for c in c64) + "\n")
             fo.write("#define GSWM_HNQ64_TAILA_COEFFS " + ", ".join(f"{float(c)!r}" for c in ca64) + "\n")
             fo.write("#define GSWM_HNQ64_TAILB_COEFFS " + ", ".join(f"{float(c)!r}" for c in cb64) + "\n")
-        print("wrote", os.path.normpath(OUT))
+        print("wrote", os.path.normpath(args.out))
 
 
 if __name__ == "__main__":
