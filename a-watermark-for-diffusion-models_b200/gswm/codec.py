@@ -191,6 +191,8 @@ def embed_batch(n_latents: int, latent_shape: Sequence[int], km: KeyMaterial, se
             out = torch.empty((n_latents, *latent_shape), dtype=torch.float32, device=dev)
         elif out.dtype != torch.float32 or out.numel() != n_latents * n or not out.is_contiguous() or out.device != dev:
             raise ValueError("out must be a contiguous fp32 tensor of n_latents * n_elems elements on the device")
+        if n_latents == 0:                       # an empty batch is valid and launches nothing
+            return out
         _lib.check(_lib.lib().gswm_embed(C.byref(dj.job), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), first_latent,
                                          out.data_ptr(), dj.ws_ptr, _stream_ptr(dev)), "gswm_embed")
         # key material / workspace are freed when dj goes out of scope; the caching allocator keeps the
@@ -235,7 +237,7 @@ class ExtractResult:
 
     def bit_accuracy(self) -> float:
         c = self.counters.cpu()
-        return float(c[0]) / float(c[1])
+        return float(c[0]) / float(c[1]) if int(c[1]) else float("nan")    # nan: no latent was scored
 
 
 def extract_batch(z: torch.Tensor, km: KeyMaterial, want_counts: bool = False,
@@ -258,6 +260,8 @@ def extract_batch(z: torch.Tensor, km: KeyMaterial, want_counts: bool = False,
         matched = torch.empty((b,), dtype=torch.int32, device=dev) if km.msgs is not None else None
         if counters is None:
             counters = torch.zeros((_lib.N_COUNTERS,), dtype=torch.int64, device=dev)
+        if b == 0:                               # an empty batch is valid and launches nothing
+            return ExtractResult(msgs, cnt, matched, counters)
         _lib.check(_lib.lib().gswm_extract(C.byref(dj.job), z.data_ptr(), _DTYPE_CODE[z.dtype], msgs.data_ptr(),
                                            cnt.data_ptr() if cnt is not None else None,
                                            matched.data_ptr() if matched is not None else None,
@@ -339,6 +343,8 @@ class HostPipe:
             raise ValueError("out must be a contiguous fp32 host array")
         b = t.shape[0]
         n = _n_elems(t.shape[1:])
+        if b == 0:
+            return out
         job, keep = self._host_job(km, b, n)
         _lib.check(_lib.lib().gswm_pipe_embed(self._p, C.byref(job), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1),
                                               first_latent, t.data_ptr()), "gswm_pipe_embed")
@@ -375,6 +381,8 @@ class HostPipe:
         cnt = np.empty((b, km.msg_bits), dtype=np.uint16) if want_counts else None
         matched = np.empty((b,), dtype=np.int32) if km.msgs is not None else None
         counters = np.zeros((_lib.N_COUNTERS,), dtype=np.int64)
+        if b == 0:
+            return msgs, cnt, matched, counters
         _lib.check(_lib.lib().gswm_pipe_extract(self._p, C.byref(job), t.data_ptr(), _DTYPE_CODE[t.dtype], msgs.ctypes.data,
                                                 cnt.ctypes.data if cnt is not None else None,
                                                 matched.ctypes.data if matched is not None else None,

@@ -667,3 +667,28 @@ def test_argument_errors(gswm, cuda_device):
     assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -2
     assert lib.gswm_embed(None, 0, 0, 0, 16, 16, None) == -1
     assert "multiple of 4" in gswm._lib.strerror(-2)
+
+
+def test_empty_batches(gswm, cuda_device):
+    """Zero latents is a valid job everywhere: nothing is launched, outputs are empty, counters stay zero."""
+    km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message("lthero", 32), 256)
+    before = gswm.launch_count()
+    z = gswm.embed_batch(0, (4, 64, 64), km, 1, device=cuda_device)
+    assert tuple(z.shape) == (0, 4, 64, 64) and z.dtype == torch.float32 and z.is_cuda
+    res = gswm.extract_batch(z, km, want_counts=True)
+    assert tuple(res.messages.shape) == (0, 32) and tuple(res.counts.shape) == (0, 256) and tuple(res.matched.shape) == (0,)
+    assert res.counters.cpu().tolist() == [0, 0, 0, 0] and res.bit_strings() == [] and np.isnan(res.bit_accuracy())
+    pipe = gswm.HostPipe(cuda_device.index or 0, max_elems=16384, chunk_latents=4)
+    out = pipe.embed(np.empty((0, 4, 64, 64), dtype=np.float32), km, 1)
+    msgs, cnt, matched, counters = pipe.extract(out, km, want_counts=True)
+    assert msgs.shape == (0, 32) and cnt.shape == (0, 256) and matched.shape == (0,) and counters.tolist() == [0, 0, 0, 0]
+    pipe.close()
+    assert gswm.launch_count() == before
+    # the C ABI itself: n_latents == 0 is success, before any launch
+    lib = gswm._lib.lib()
+    flat = torch.zeros(96, dtype=torch.uint8, device=cuda_device)
+    buf = torch.zeros(64, dtype=torch.float32, device=cuda_device)
+    job = gswm._lib.Job(0, 16384, 256, 0, flat.data_ptr(), flat.data_ptr() + 32, flat.data_ptr() + 48)
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, buf.data_ptr(), None, None) == 0
+    assert lib.gswm_extract(C.byref(job), buf.data_ptr(), 0, flat.data_ptr(), None, None, None, None, None) == 0
+    assert gswm.launch_count() == before
