@@ -692,3 +692,28 @@ def test_empty_batches(gswm, cuda_device):
     assert lib.gswm_embed(C.byref(job), 0, 0, 0, buf.data_ptr(), None, None) == 0
     assert lib.gswm_extract(C.byref(job), buf.data_ptr(), 0, flat.data_ptr(), None, None, None, None, None) == 0
     assert gswm.launch_count() == before
+
+
+@pytest.mark.parametrize("shape,L", [((4, 96, 64), 96), ((4, 8, 16), 32), ((4, 152, 104), 256), ((4, 128, 128), 1024)])
+def test_per_latent_keys_on_ragged_and_multi_tile_latents(gswm, cuda_device, shape, L):
+    """Distinct key / nonce / message per latent on shapes that are not one whole tile: partial last tile, less than one
+    ChaCha block row, several tiles -- embed against the oracle, extract counts and messages against the oracle."""
+    rs = np.random.RandomState(int(np.prod(shape)) + L)
+    b, n = 9, int(np.prod(shape))
+    keys = [rs.bytes(32) for _ in range(b)]
+    nonces = [rs.bytes(16) for _ in range(b)]
+    msgs = [rs.bytes(L // 8) for _ in range(b)]
+    km = gswm.KeyMaterial.make(b"".join(keys), b"".join(nonces), b"".join(msgs), L)
+    z = gswm.embed_batch(b, shape, km, 5, 0, 40, cuda_device)
+    zh = z.cpu().numpy().reshape(b, n)
+    ref = oracle_embed_batch(msgs, keys, nonces, n, L, 5, 0, 40, b)
+    assert np.array_equal(zh >= 0, ref >= 0)
+    assert rel_err(zh, ref).max() <= REL_TOL
+    if n % L == 0:
+        noisy = (z + 2.0 * torch.randn(z.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(3))).clamp(max=8.0)
+        res = gswm.extract_batch(noisy, km, want_counts=True)
+        nh = noisy.cpu().numpy().reshape(b, n)
+        for i in range(b):
+            assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(nh[i], keys[i], nonces[i], L)), i
+            assert O.bits_to_bytes(O.recover_message_bits(nh[i], keys[i], nonces[i], L)) == res.messages[i].cpu().numpy().tobytes()
+        assert gswm.extract_batch(z, km).messages.cpu().numpy().tobytes() == b"".join(msgs)
