@@ -717,3 +717,32 @@ def test_per_latent_keys_on_ragged_and_multi_tile_latents(gswm, cuda_device, sha
             assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(nh[i], keys[i], nonces[i], L)), i
             assert O.bits_to_bytes(O.recover_message_bits(nh[i], keys[i], nonces[i], L)) == res.messages[i].cpu().numpy().tobytes()
         assert gswm.extract_batch(z, km).messages.cpu().numpy().tobytes() == b"".join(msgs)
+
+
+def test_large_latent_index_seed_offset_and_longest_message(gswm, cuda_device):
+    """64-bit corners of the uniform source (global latent index 2^40, full-width seed, offset just below 2^62) against the
+    oracle, and the longest message the extract kernel takes (8192 bits); one more bit is a range error, not a launch."""
+    shape, n, L = (4, 128, 128), 65536, 256
+    msg = gswm.pad_message("lthero", 32)
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, L)
+    seed, offset, first = 0xFEDCBA9876543210, (1 << 62) - 5, (1 << 40) + 7
+    z = gswm.embed_batch(2, shape, km, seed, offset, first, cuda_device).cpu().numpy().reshape(2, n)
+    for i in range(2):
+        ref = O.embed_gswm("lthero", KEY, NONCE, seed, offset, first + i, n, L)
+        assert np.array_equal(z[i] >= 0, ref >= 0) and rel_err(z[i], ref).max() <= REL_TOL
+    with pytest.raises(gswm.GswmError):
+        gswm.embed_batch(1, shape, km, seed, 1 << 62, 0, cuda_device)      # offset >= 2^62 is out of range
+
+    L = 8192
+    rs = np.random.RandomState(8192)
+    big = rs.bytes(L // 8)
+    km = gswm.KeyMaterial.make(KEY, NONCE, big, L)
+    zz = gswm.embed_batch(3, shape, km, 1, 0, 0, cuda_device)
+    noisy = (zz + 0.8 * torch.randn(zz.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(9))).clamp(max=8.0)
+    res = gswm.extract_batch(noisy, km, want_counts=True)
+    nh = noisy.cpu().numpy().reshape(3, n)
+    for i in range(3):
+        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(nh[i], KEY, NONCE, L))
+    assert gswm.extract_batch(zz, km).messages.cpu().numpy().tobytes() == big * 3
+    with pytest.raises(gswm.GswmError):
+        gswm.extract_batch(torch.zeros((1, 4, 128, 128), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 16384))
