@@ -17,16 +17,15 @@
 #include <cstdlib>
 
 #include "../../include/gswm.h"
+#include "gswm_comm.cuh"
+#include "gswm_internal.h"
 #include "gswm_math.cuh"
+#include "gswm_tile.cuh"
 
 namespace gswm {
 
-constexpr int kThreads = 256;
-constexpr int kTileElems = 16384;            // 32 ChaCha blocks
-constexpr int kTileWords = kTileElems / 32;  // 512 keystream words
-constexpr int kTileF4 = kTileElems / 4;      // 4096 float4 per tile
-
 static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // Reference extract.py:83: int(norm.cdf(z) * 2) == 1  <=>  z >= -6.957291061679417e-17 (float64).
 // Smallest fp32 that is >= that double (0xA4A06C98); bf16 inputs use its truncation 0xA4A0, fp16 inputs +0 (no fp16
@@ -40,24 +39,6 @@ __device__ __forceinline__ float quantise_threshold() { return __uint_as_float(0
 // latency and the CTA prologue (sign table, barrier init, counter reset): ~2-3 us per kernel of a ~60 us step.
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-__device__ __forceinline__ void load_key_nonce(const uint8_t* __restrict__ keys, const uint8_t* __restrict__ nonces,
-                                               int64_t row, uint32_t (&k)[8], uint32_t (&n)[4]) {
-  const uint32_t* kp = reinterpret_cast<const uint32_t*>(keys + row * 32);
-  const uint32_t* np = reinterpret_cast<const uint32_t*>(nonces + row * 16);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) k[i] = __ldg(kp + i);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) n[i] = __ldg(np + i);
-}
-
-// Message word for keystream word index `wi` of a latent: the message tiled n_elems/msg_bits times,
-// zero beyond the last whole copy (nodes.py:79-87).
-__device__ __forceinline__ uint32_t tiled_msg_word(const uint8_t* __restrict__ msg, uint32_t wi, uint32_t msg_words,
-                                                   uint32_t tiled_words) {
-  if (msg == nullptr || wi >= tiled_words) return 0u;
-  return __ldg(reinterpret_cast<const uint32_t*>(msg) + (wi % msg_words));
-}
 
 // ------------------------------------------------------------------------------------------------
 // K1: keystream (optionally XOR tiled message) to global memory, one ChaCha block per thread.
@@ -88,54 +69,6 @@ chacha20_keystream_kernel(const uint8_t* __restrict__ keys, const uint8_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile keystream staging.  A CTA always computes the keystream it needs itself, into its own shared memory, one
-// ChaCha20 block per lane:
-//   shared key      : once per CTA, AHEAD of the grid dependency wait (key material is final before the call is
-//                     enqueued, gswm.h), so that behind another kernel the predecessor's tail hides it.  An earlier
-//                     version computed one table per launch in global memory and had every CTA wait on a ready flag:
-//                     4.1 us of whole-GPU idle per launch (tools/embed_trace.py) against 0 (hidden) .. 2.4 us (cold).
-//   per-latent keys : once per latent and tile, by warp 0 between two barriers.
-// ------------------------------------------------------------------------------------------------
-// lane `lane` of one warp: ChaCha block `tile*32 + lane` of stream `row`, XOR tiled message, 64 bytes to dst
-__device__ __forceinline__ void chacha_tile_lane(uint32_t* __restrict__ dst, const uint8_t* __restrict__ keys,
-                                                 const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
-                                                 int64_t row, uint32_t tile, uint32_t lane, uint32_t msg_words,
-                                                 uint32_t tiled_words) {
-  uint32_t k[8], n[4], ks[16];
-  load_key_nonce(keys, nonces, row, k, n);
-  const uint32_t blk = tile * 32 + lane;
-  chacha20_block(k, n, blk, ks);
-  uint4* d4 = reinterpret_cast<uint4*>(dst + lane * 16);     // lane l owns words [16 l, 16 l + 16)
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 v;
-    v.x = ks[4 * q + 0] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 0, msg_words, tiled_words);
-    v.y = ks[4 * q + 1] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 1, msg_words, tiled_words);
-    v.z = ks[4 * q + 2] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 2, msg_words, tiled_words);
-    v.w = ks[4 * q + 3] ^ tiled_msg_word(msg, blk * 16 + 4 * q + 3, msg_words, tiled_words);
-    d4[q] = v;
-  }
-}
-
-// elements of tile `tile` of an n_elems-element latent (n_elems is a multiple of 4, not necessarily of the tile)
-__device__ __forceinline__ uint32_t tile_elems(int64_t n_elems, uint32_t tile) {
-  const int64_t remain = n_elems - (int64_t)tile * kTileElems;
-  return (uint32_t)(remain < kTileElems ? remain : kTileElems);
-}
-// keystream words covering them (a trailing partial word / partial ChaCha block is computed whole)
-__device__ __forceinline__ uint32_t tile_words(int64_t n_elems, uint32_t tile) { return (tile_elems(n_elems, tile) + 31u) >> 5; }
-
-// Warp 0 computes tile `tile` of stream `row` in place (per-latent keys: row = latent; shared key: row = 0).
-__device__ __forceinline__ void compute_private_slice(uint32_t* __restrict__ s_ks, const uint8_t* __restrict__ keys,
-                                                      const uint8_t* __restrict__ nonces, const uint8_t* __restrict__ msg,
-                                                      int64_t latent, uint32_t tile, uint32_t words, uint32_t msg_words,
-                                                      uint32_t tiled_words) {
-  if (threadIdx.x < 32 && threadIdx.x * 16 < words)
-    chacha_tile_lane(s_ks, keys, nonces, msg, latent, tile, threadIdx.x, msg_words, tiled_words);
-  __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
 // K2: embed.  grid = n_latents * tiles_per_latent CTAs, one tile each.
 //   bits  <- keystream XOR tiled message                                (gs_insert.py:23,45-49)
 //   u     <- 23 bits of Philox4x32 per element (3 calls feed 16 elements) (stands in for gs_insert.py:62)
@@ -155,6 +88,7 @@ struct EmbedArgs {
   uint32_t tiled_words;
   uint32_t msg_stride_bytes;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;   // off_hi holds (offset_hi << 2): its low 2 bits select the Philox call
+  uint32_t keys_in_flight;   // GSWM_JOB_KEYS_IN_FLIGHT: read key material only behind the grid dependency wait
   PhiloxKeys rk;             // round keys of (seed_lo, seed_hi)
 };
 
@@ -174,11 +108,11 @@ __device__ __forceinline__ void build_sign_lut(float4* lut) {
   lut[2 * b + 1] = make_float4((b & 0x08u) ? 1.f : -1.f, (b & 0x04u) ? 1.f : -1.f, (b & 0x02u) ? 1.f : -1.f, (b & 0x01u) ? 1.f : -1.f);
 }
 
+#ifndef GSWM_TOPCELL
+#define GSWM_TOPCELL 1
+#endif
 #ifndef GSWM_PHILOX_CONST_KEYS
 #define GSWM_PHILOX_CONST_KEYS 1
-#endif
-#ifndef GSWM_EMIT_PAIRS
-#define GSWM_EMIT_PAIRS 0
 #endif
 // One SUPER-ITERATION of a tile: 1024 float4 = 4 per thread, fed by three Philox calls.
 // Philox counter word 0..1: G = ((global_latent * tiles + tile) * 4 + sidx) * 256 + tid; words 2..3: offset, call index.
@@ -206,20 +140,6 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
   const uint32_t f2[4] = {fbits_top23(c2.x), fbits_top23(c2.y), fbits_top23(c2.z), fbits_top23(c2.w)};
   const uint32_t f3[4] = {fbits_low_bytes(c0.x, c1.x, c2.x), fbits_low_bytes(c0.y, c1.y, c2.y),
                           fbits_low_bytes(c0.z, c1.z, c2.z), fbits_low_bytes(c0.w, c1.w, c2.w)};
-#if GSWM_EMIT_PAIRS
-  // two float4 per call: bucket bits of elements 4i..4i+3 are byte i>>1 of the tile's (keystream ^ message), high nibble first
-  auto emit2 = [&](uint32_t ia, uint32_t ib, const uint32_t (&fa)[4], const uint32_t (&fb)[4]) {
-    if (kGuard && ia >= n_f4) return;
-    const float4 sa = my_sign[2u * s_bytes[ia >> 1]];
-    const float4 sb = my_sign[2u * s_bytes[(kGuard && ib >= n_f4 ? ia : ib) >> 1]];
-    float4 za, zb;
-    bucket_quantile8_f32(fa, fb, sa, sb, za, zb);
-    __stcs(out4 + ia, za);                                            // streaming store: written once, never re-read
-    if (!kGuard || ib < n_f4) __stcs(out4 + ib, zb);
-  };
-  emit2(i0, i0 + kThreads, f0, f1);
-  emit2(i0 + 2 * kThreads, i0 + 3 * kThreads, f2, f3);
-#else
   auto emit = [&](uint32_t i, const uint32_t (&f)[4], uint32_t k) {
     if (kGuard && i >= n_f4) return;
 #ifdef GSWM_WHATIF_NOSIGN
@@ -229,27 +149,32 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
                                                                     __byte_perm(sign_pack, 0u, 0x4440u | k))
                                 : my_sign[2u * s_bytes[i >> 1]];
 #endif
+    // uniforms v3: an element in the outermost grid cell draws its refinement from Philox call 3 of this counter, key word 1 + k
+#if GSWM_TOPCELL
+    const TopCellRefine top{g_tile, sidx * kThreads, a.off_lo, a.off_hi, a.seed_lo, a.seed_hi, k};
+#else
+    const NoTopCell top;                                               // diagnostic build (uniforms v2: the cell's midpoint)
+#endif
 #ifdef GSWM_WHATIF_NOSTORE
-    const float4 zq = bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn);
+    const float4 zq = bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn, top);
     if (zq.x == 123.456f) __stcs(out4 + i, zq);                        // diagnostic build: arithmetic kept alive, nothing written
 #else
-    __stcs(out4 + i, bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn));   // !kGuard: every lane of the warp is here
+    __stcs(out4 + i, bucket_quantile4_f32<!kGuard>(f[0], f[1], f[2], f[3], sgn, top));   // !kGuard: every lane of the warp is here
 #endif
   };
   emit(i0, f0, 0);
   emit(i0 + kThreads, f1, 1);
   emit(i0 + 2 * kThreads, f2, 2);
   emit(i0 + 3 * kThreads, f3, 3);
-#endif
 }
 
-// Grid (X, Y).  CTA (x, y) owns one fixed piece of the latent layout -- so its 2 KB of (keystream ^ message), its
-// sign LUT and its Philox offset are set up ONCE -- and walks the latents x, x + X, x + 2X, ...
+// Grid (X, Y).  CTA (x, y) owns one fixed piece of the latent layout -- so its keystream, its sign table and its Philox
+// offset are set up ONCE -- and walks the latents x, x + X, x + 2X, ...
 //   shared key : Y = non-empty HALF tiles of a latent; CTA (x, h) produces super-iterations {2(h&1), 2(h&1)+1} of tile
 //                h>>1 (two independent instruction streams).  X * Y is sized to the CTAs the GPU holds at once
-//                (persistent); nothing in the latent loop synchronises, warps drift freely.  CTA (0, 2t) computes slice
-//                t of the shared table, every CTA of tile t acquires it (the producer has the lowest linear index of its
-//                consumers, so it is dispatched no later than any of them and never waits itself).
+//                (persistent); nothing in the latent loop synchronises, warps drift freely.  Every CTA computes the 16
+//                ChaCha20 blocks of ITS half tile itself, into its own shared memory, ahead of the grid dependency wait:
+//                there is no cross-CTA dependency of any kind (see "Tile keystream staging" above).
 //   per-latent : Y = tiles, X = n_latents (one latent per CTA): warp 0 computes the tile's keystream between two barriers
 //                while the SM's other CTAs keep its issue slots busy.
 // Resident CTAs per SM.  Shared key: 4 (64 registers: two super-iterations in flight without spills; measured 69.7 us per
@@ -299,9 +224,14 @@ embed_kernel(const EmbedArgs a) {
     // Shared key: this CTA's half tile needs 16 ChaCha20 blocks, once.  Half a warp computes them here, AHEAD of the
     // grid dependency wait -- key material is final before the call is enqueued (gswm.h) -- so when the previous kernel
     // in the stream is still draining, its tail hides this prologue; no table in global memory, no flag to spin on.
+    // (GSWM_JOB_KEYS_IN_FLIGHT: the key material may still be being written -- same thing, behind the wait.)
     const uint32_t lane = threadIdx.x;
-    if (lane < 32 && (lane >> 4) == (blockIdx.y & 1u) && lane * 16 < words)
-      chacha_tile_lane(s_ks, a.keys, a.nonces, a.msgs, 0, tile, lane, a.msg_words, a.tiled_words);
+    const bool mine = lane < 32 && (lane >> 4) == (blockIdx.y & 1u) && lane * 16 < words;
+    if (mine && !a.keys_in_flight) chacha_tile_lane(s_ks, a.keys, a.nonces, a.msgs, 0, tile, lane, a.msg_words, a.tiled_words);
+    if (a.keys_in_flight) {
+      griddep_wait();
+      if (mine) chacha_tile_lane(s_ks, a.keys, a.nonces, a.msgs, 0, tile, lane, a.msg_words, a.tiled_words);
+    }
     __syncthreads();                                                  // LUT + keystream visible
   }
   griddep_wait();                                                     // nothing above writes global memory or reads a predecessor's output
@@ -414,6 +344,11 @@ struct ExtractArgs {
   uint32_t msg_stride_bytes;
   uint32_t copies;            // R = n_elems / msg_bits
   uint32_t ks_cache_tiles;    // shared-key mode: tiles of keystream kept resident in shared memory (0 = restage per tile)
+  uint8_t* flags;             // per-latent GSWM_FLAG_* (may be null)
+  uint32_t keys_in_flight;    // GSWM_JOB_KEYS_IN_FLIGHT: read key material only behind the grid dependency wait
+  // gswm_extract_allreduce: the last CTA to retire sums `counters` over the ranks of `comm` into `reduced`
+  long long* reduced;         // null = plain extract
+  CommDev comm;
 };
 
 #ifndef GSWM_CHUNK_BYTES
@@ -475,6 +410,24 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uin
 
 // Quantise the four elements of group g of a staged chunk to a word with the NEGATED reference bit of element j
 // in bit 7 of byte j.  The reference's bit is int(norm.cdf(z) * 2) == (z >= T), T = quantise_threshold() (tiny, < 0).
+//
+// The same pass keeps, per thread, a NaN-PROPAGATING running maximum of every element it has seen of the current latent
+// (`scan`): extract.py:83 raises for a NaN (int(nan)) and extract.py:86 for any z >= 8.292361075813597 (int(cdf * 2) == 2),
+// and the end-of-latent code turns that maximum into the latent's GSWM_FLAG_* -- two FMNMX3.NAN per four fp32 elements
+// (two HMNMX2.NAN for 16-bit inputs) instead of two extra passes over the tensor on the host side of the drop-in.
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// smallest value of each type that is >= 8.292361075813597 (where int(norm.cdf(z) * 2) becomes 2)
+__device__ __forceinline__ float range_limit_f32() { return __uint_as_float(0x4104AD83u); }   // 8.29236125946045
+constexpr float kRangeLimitF16 = 8.296875f;                                                    // 0x4826
+constexpr float kRangeLimitBF16 = 8.3125f;                                                     // 0x4105
+__device__ __forceinline__ uint32_t range_flags(float running_max, float limit) {
+  return running_max != running_max ? (uint32_t)GSWM_FLAG_NAN : (running_max >= limit ? (uint32_t)GSWM_FLAG_RANGE : 0u);
+}
+
 template <typename T>
 struct NegatedBits;
 
@@ -483,8 +436,14 @@ struct NegatedBits;
 // including -0.0 and the [T, 0) sliver, which extract.py:83 maps to 1.  Three byte permutes gather the sign bytes.
 template <>
 struct NegatedBits<float> {
-  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g) {
+  struct Scan {
+    float m;
+    __device__ __forceinline__ void reset() { m = -CUDART_INF_F; }
+    __device__ __forceinline__ uint32_t flags() const { return range_flags(m, range_limit_f32()); }
+  };
+  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g, Scan& scan) {
     const float4 z = reinterpret_cast<const float4*>(stage)[g];
+    scan.m = fmax3_nan(z.x, z.y, fmax3_nan(z.z, z.w, scan.m));
     const float c = -quantise_threshold();
     const uint32_t s0 = __float_as_uint(z.x + c), s1 = __float_as_uint(z.y + c);
     const uint32_t s2 = __float_as_uint(z.z + c), s3 = __float_as_uint(z.w + c);
@@ -500,34 +459,56 @@ struct NegatedBits<float> {
 //          the reference needs (norm.cdf(-0.0) * 2 == 1);
 //   bf16 : has fp32's exponent range, so tiny negatives in [T, 0) exist and must decode as 1: T16 = 0xA4A0
 //          (-6.94e-17, the fp32 threshold's bit pattern truncated towards zero).  Subnormals are compared, not flushed.
-template <typename T2, uint32_t kThresholdBits>
+template <typename T2, uint32_t kThresholdBits, bool kHalf>
 struct NegatedBits16 {
-  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g) {
+  struct Scan {
+    T2 m;
+    __device__ __forceinline__ void reset() {
+      const uint32_t ninf = kHalf ? 0xFC00FC00u : 0xFF80FF80u;       // -inf x2 (fp16 | bf16)
+      memcpy(&m, &ninf, 4);
+    }
+    __device__ __forceinline__ uint32_t flags() const {
+      float2 f;
+      if constexpr (kHalf) f = __half22float2(m); else f = __bfloat1622float2(m);
+      const float limit = kHalf ? kRangeLimitF16 : kRangeLimitBF16;
+      return range_flags(f.x, limit) | range_flags(f.y, limit);      // NAN | RANGE collapses to NAN in the caller
+    }
+  };
+  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g, Scan& scan) {
     const uint2 r = reinterpret_cast<const uint2*>(stage)[g];
     const uint32_t tb = kThresholdBits | (kThresholdBits << 16);
     T2 zx, zy, thr;
     memcpy(&zx, &r.x, 4);
     memcpy(&zy, &r.y, 4);
     memcpy(&thr, &tb, 4);
+    scan.m = __hmax2_nan(scan.m, __hmax2_nan(zx, zy));
     const uint32_t nx = __hlt2_mask(zx, thr);                         // 0xFFFF per halfword where z < T16
     const uint32_t ny = __hlt2_mask(zy, thr);
     return __byte_perm(nx, ny, 0x7531);                              // bytes: x.b1, x.b3, y.b1, y.b3
   }
 };
-// fp64 (what gs_insert.py:75 returns and a float64 caller hands to extract.py:83): the reference's own threshold, compared
+// fp64 (what gs_insert.py:75 returns and a float64 caller hands to extract.py:83): the reference's own thresholds, compared
 // in double.  Not a throughput path (fp64 compares run at 1/64 rate); it keeps float64 callers on the device.
 template <>
 struct NegatedBits<double> {
-  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g) {
+  struct Scan {
+    uint32_t f;
+    __device__ __forceinline__ void reset() { f = 0; }
+    __device__ __forceinline__ uint32_t flags() const { return f; }
+  };
+  static __device__ __forceinline__ uint32_t word(const void* stage, uint32_t g, Scan& scan) {
     const double2 a = reinterpret_cast<const double2*>(stage)[2 * g], b = reinterpret_cast<const double2*>(stage)[2 * g + 1];
     const double t = -6.957291061679417e-17;                          // int(norm.cdf(z) * 2) == 1  <=>  z >= t
+    const double big = 8.292361075813597;                             // int(norm.cdf(z) * 2) == 2  <=>  z >= big
+    if (a.x != a.x || a.y != a.y || b.x != b.x || b.y != b.y) scan.f |= GSWM_FLAG_NAN;
+    if (a.x >= big || a.y >= big || b.x >= big || b.y >= big) scan.f |= GSWM_FLAG_RANGE;
     return (a.x < t ? 0x00000080u : 0u) | (a.y < t ? 0x00008000u : 0u) | (b.x < t ? 0x00800000u : 0u) | (b.y < t ? 0x80000000u : 0u);
   }
 };
 template <>
-struct NegatedBits<__half> : NegatedBits16<__half2, 0x0000u> {};
+struct NegatedBits<__half> : NegatedBits16<__half2, 0x0000u, true> {};
 template <>
-struct NegatedBits<__nv_bfloat16> : NegatedBits16<__nv_bfloat162, 0xA4A0u> {};
+struct NegatedBits<__nv_bfloat16> : NegatedBits16<__nv_bfloat162, 0xA4A0u, false> {};
 
 template <typename T, bool kPerLatent, bool kPow2>
 __global__ void __launch_bounds__(kThreads, (Ring<T, kPerLatent>::kMinBlocks))
@@ -541,6 +522,7 @@ extract_kernel(const ExtractArgs a) {
   uint32_t* s_cnt = s_ks_all + (a.ks_cache_tiles ? a.ks_cache_tiles : 1u) * kTileWords;  // msg_bits counters
   __shared__ __align__(8) uint64_t s_full[kStages];
   __shared__ int s_matched;
+  __shared__ uint32_t s_flags;
 
   const uint32_t cpl = a.chunks_per_latent;
   // byte * magic puts the thread's keystream nibble (MSB = element 0) on bit 7 of bytes 0..3; the other nibble's
@@ -566,6 +548,14 @@ extract_kernel(const ExtractArgs a) {
     mbar_expect_tx(bar, bytes);
     tma_load_1d(s_stage + (size_t)(q % kStages) * kStageBytes, src, bytes, bar, policy);
   };
+  // Shared key, a latent's whole keystream fits the cache: every CTA computes it once, warp w taking tiles w, w + 8, ...
+  auto stage_resident_keystream = [&]() {
+    for (uint32_t t = threadIdx.x >> 5; t < a.ks_cache_tiles; t += kThreads / 32) {
+      const uint32_t lane = threadIdx.x & 31u;
+      if (lane * 16 < tile_words(a.n_elems, t))
+        chacha_tile_lane(s_ks_all + t * kTileWords, a.keys, a.nonces, nullptr, 0, t, lane, 0, 0);
+    }
+  };
 
   griddep_launch_dependents();
   if (threadIdx.x == 0) {
@@ -573,24 +563,25 @@ extract_kernel(const ExtractArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     s_matched = 0;
+    s_flags = 0;
   }
   for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) s_cnt[p] = 0;
-  if constexpr (!kPerLatent) {
-    // Shared key, a latent's whole keystream fits the cache: every CTA computes it once, warp w taking tiles w, w + 8, ..,
-    // ahead of the grid dependency wait (key material is final before the call is enqueued, gswm.h).
-    for (uint32_t t = threadIdx.x >> 5; t < a.ks_cache_tiles; t += kThreads / 32) {
-      const uint32_t lane = threadIdx.x & 31u;
-      if (lane * 16 < tile_words(a.n_elems, t))
-        chacha_tile_lane(s_ks_all + t * kTileWords, a.keys, a.nonces, nullptr, 0, t, lane, 0, 0);
-    }
-  }
+  // ... ahead of the grid dependency wait: key material is final before the call is enqueued (gswm.h) unless the job says
+  // GSWM_JOB_KEYS_IN_FLIGHT
+  if (!kPerLatent && !a.keys_in_flight) stage_resident_keystream();
   __syncthreads();
   griddep_wait();                                                     // nothing above writes global memory or reads a predecessor's output
+  if (!kPerLatent && a.keys_in_flight) {
+    stage_resident_keystream();
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     for (int64_t q = 0; q < kStages - 1; ++q) issue(q);               // kStages-1 chunks in flight from the start
   }
 
-  unsigned long long acc_matched = 0, acc_exact = 0, acc_msgs = 0;   // thread 0 only; flushed once per CTA
+  unsigned long long acc_matched = 0, acc_exact = 0, acc_msgs = 0, acc_nan = 0, acc_range = 0;   // thread 0 only; flushed once per CTA
+  const uint32_t row_bytes = a.msg_stride_bytes;                     // (msg_bits + 7) / 8
+  const bool whole_words = (a.msg_bits & 31u) == 0;                  // message rows are whole, aligned 32-bit words
 
   int64_t q = 0;                                 // flat chunk index
   for (int64_t seq = 0; seq < n_mine; ++seq) {
@@ -598,6 +589,8 @@ extract_kernel(const ExtractArgs a) {
     uint32_t packed = 0;                          // kPow2: byte lane k = count of element k
     uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;      // spilled byte lanes (only for very large latents)
     uint32_t adds_since_spill = 0;
+    typename NegatedBits<T>::Scan scan;           // NaN-propagating running maximum of this thread's elements of the latent
+    scan.reset();
 
     for (uint32_t within = 0; within < cpl; ++within, ++q) {
       // every thread has finished chunk q-1 (barrier at the end of the previous iteration): refill its slot
@@ -613,7 +606,7 @@ extract_kernel(const ExtractArgs a) {
       const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
       const int64_t e0 = (int64_t)within * kChunkElems;
       const int64_t rem = a.n_elems - e0;
-      const uint32_t n_grp = (uint32_t)(rem < kChunkElems ? rem : kChunkElems) >> 2;   // multiple of 8 (msg_bits | n_elems)
+      const uint32_t n_grp = (uint32_t)(rem < kChunkElems ? rem : kChunkElems) >> 2;
       mbar_wait(&s_full[q % kStages], (uint32_t)((q / kStages) & 1));
       const unsigned char* stage = s_stage + (size_t)(q % kStages) * kStageBytes;
       // keystream nibble of group i of the tile lives in byte i>>1 (high nibble for even i); this thread's groups
@@ -622,17 +615,19 @@ extract_kernel(const ExtractArgs a) {
       const uint8_t* ks_base = s_bytes + chunk_in_tile * (kChunkElems / 8) + (threadIdx.x >> 1);
       auto consume = [&](uint32_t k) {
         const uint32_t g = k * kThreads + threadIdx.x;
-        const uint32_t nz = NegatedBits<T>::word(stage, g);
+        const uint32_t nz = NegatedBits<T>::word(stage, g, scan);
         const uint32_t ks = (uint32_t)ks_base[k * (kThreads / 2)] * spread_magic;
         const uint32_t d = ~(nz ^ ks) & 0x80808080u;                   // decrypted bit of element j in bit 7 of byte j
         if constexpr (kPow2) {
           packed += d >> 7;
         } else {
-          const uint32_t pos = (uint32_t)((e0 + 4 * (int64_t)g) % a.msg_bits);
-          if (d & 0x00000080u) atomicAdd(&s_cnt[pos + 0], 1u);
-          if (d & 0x00008000u) atomicAdd(&s_cnt[pos + 1], 1u);
-          if (d & 0x00800000u) atomicAdd(&s_cnt[pos + 2], 1u);
-          if (d & 0x80000000u) atomicAdd(&s_cnt[pos + 3], 1u);
+          // any message length that divides the latent (extract.py:91-98): element e votes for position e % msg_bits
+          uint32_t pos = (uint32_t)((e0 + 4 * (int64_t)g) % a.msg_bits);
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            if (d & (0x80u << (8u * j))) atomicAdd(&s_cnt[pos], 1u);
+            if (++pos == a.msg_bits) pos = 0;
+          }
         }
       };
       if (n_grp == kChunkElems / 4) {
@@ -653,6 +648,12 @@ extract_kernel(const ExtractArgs a) {
     }
 
     // ---- end of latent: majority vote, pack MSB-first, score against the reference message ----
+    {
+      // the inputs the reference rejects: any thread's running maximum is NaN or >= 8.2924 (one shared-memory OR per warp that saw one)
+      const uint32_t f = scan.flags();
+      const uint32_t any = __reduce_or_sync(0xFFFFFFFFu, f);
+      if (any && (threadIdx.x & 31u) == 0) atomicOr(&s_flags, any);
+    }
     if constexpr (kPow2) {
       c0 += packed & 0xFF; c1 += (packed >> 8) & 0xFF; c2 += (packed >> 16) & 0xFF; c3 += packed >> 24;
       const uint32_t pos = (4u * threadIdx.x) & (a.msg_bits - 1u);
@@ -660,36 +661,70 @@ extract_kernel(const ExtractArgs a) {
       atomicAdd(&s_cnt[pos + 1], c1);
       atomicAdd(&s_cnt[pos + 2], c2);
       atomicAdd(&s_cnt[pos + 3], c3);
-      __syncthreads();
     }
-    const uint8_t* ref = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)a.msg_stride_bytes : 0) : nullptr;
+    __syncthreads();                              // counts and flags of the whole latent are in shared memory
+    const uint8_t* ref = a.msgs ? a.msgs + (kPerLatent ? latent * (int64_t)row_bytes : 0) : nullptr;
+    uint8_t* out_row = a.msg_out + latent * (int64_t)row_bytes;
     int my_matched = 0;
-    for (uint32_t p = threadIdx.x; p < a.msg_bits; p += kThreads) {   // msg_bits % 32 == 0: whole warps
-      const uint32_t cnt = s_cnt[p];
-      s_cnt[p] = 0;                                                    // ready for the next latent
-      if (a.counts) a.counts[latent * a.msg_bits + p] = (uint16_t)cnt;
-      const bool bit = 2u * cnt > a.copies;                            // count_1 > len(segments)/2
+    for (uint32_t p0 = 0; p0 < a.msg_bits; p0 += kThreads) {          // uniform trip count: whole warps reach the ballot
+      const uint32_t p = p0 + threadIdx.x;
+      const bool valid = p < a.msg_bits;
+      uint32_t cnt = 0;
+      if (valid) {
+        cnt = s_cnt[p];
+        s_cnt[p] = 0;                                                  // ready for the next latent
+        if (a.counts) a.counts[latent * a.msg_bits + p] = (uint16_t)cnt;
+      }
+      const bool bit = valid && 2u * cnt > a.copies;                   // count_1 > len(segments)/2; tie -> 0 (extract.py:99)
       const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);         // lane l = position 32w + l
       // position l of the word -> byte l>>3, bit 7-(l&7): reverse all bits, then swap bytes back
       const uint32_t word = __byte_perm(__brev(ballot), 0u, 0x0123);
-      if ((threadIdx.x & 31) == 0) {
-        reinterpret_cast<uint32_t*>(a.msg_out + latent * (int64_t)(a.msg_bits >> 3))[p >> 5] = word;
-        if (ref) my_matched += __popc(~(word ^ __ldg(reinterpret_cast<const uint32_t*>(ref) + (p >> 5))));
+      const uint32_t wbase = p & ~31u;                                 // first position of this warp's word
+      if ((threadIdx.x & 31) == 0 && wbase < a.msg_bits) {
+        if (whole_words) {
+          reinterpret_cast<uint32_t*>(out_row)[wbase >> 5] = word;
+          if (ref) my_matched += __popc(~(word ^ __ldg(reinterpret_cast<const uint32_t*>(ref) + (wbase >> 5))));
+        } else {
+          // a row is (msg_bits + 7) / 8 bytes at any alignment: byte stores; bits past msg_bits are zero and not scored
+          const uint32_t left = a.msg_bits - wbase;                    // valid positions in this word (>= 1)
+          const uint32_t nb = left >= 32u ? 4u : (left + 7u) >> 3;
+          uint32_t refw = 0;
+          for (uint32_t b = 0; b < nb; ++b) {
+            out_row[(wbase >> 3) + b] = (uint8_t)(word >> (8u * b));
+            if (ref) refw |= (uint32_t)ref[(wbase >> 3) + b] << (8u * b);
+          }
+          if (ref) {
+            uint32_t mask = 0;                                         // position l valid <=> l < left; byte b holds l = 8b .. 8b+7 MSB-first
+            for (uint32_t b = 0; b < nb; ++b) {
+              const uint32_t v = left - 8u * b >= 8u ? 8u : left - 8u * b;
+              mask |= ((0xFF00u >> v) & 0xFFu) << (8u * b);
+            }
+            my_matched += __popc(~(word ^ refw) & mask);
+          }
+        }
       }
     }
     if (ref) {
       if ((threadIdx.x & 31) == 0 && my_matched) atomicAdd(&s_matched, my_matched);
       __syncthreads();
-      if (threadIdx.x == 0) {
+    }
+    if (threadIdx.x == 0) {
+      uint32_t f = s_flags;
+      s_flags = 0;
+      if (f & GSWM_FLAG_NAN) f = GSWM_FLAG_NAN;                        // int(nan) raises before the digit string is parsed
+      if (a.flags) a.flags[latent] = (uint8_t)f;
+      acc_nan += (unsigned long long)(f == GSWM_FLAG_NAN);
+      acc_range += (unsigned long long)(f == GSWM_FLAG_RANGE);
+      if (ref) {
         const int m = s_matched;
         s_matched = 0;
         if (a.matched) a.matched[latent] = m;
         acc_matched += (unsigned long long)m;
         acc_exact += (unsigned long long)(m == (int)a.msg_bits);
       }
+      ++acc_msgs;
     }
-    if (threadIdx.x == 0) ++acc_msgs;
-    __syncthreads();                              // s_cnt / s_matched reset visible before the next latent
+    __syncthreads();                              // s_cnt / s_matched / s_flags reset visible before the next latent
   }
   if (threadIdx.x == 0 && a.counters && acc_msgs) {
     if (a.msgs) {
@@ -698,7 +733,45 @@ extract_kernel(const ExtractArgs a) {
     }
     atomicAdd(&a.counters[GSWM_CTR_TOTAL_BITS], acc_msgs * a.msg_bits);
     atomicAdd(&a.counters[GSWM_CTR_TOTAL_MSGS], acc_msgs);
+    if (acc_nan) atomicAdd(&a.counters[GSWM_CTR_NAN_LATENTS], acc_nan);
+    if (acc_range) atomicAdd(&a.counters[GSWM_CTR_RANGE_LATENTS], acc_range);
   }
+
+  // ---- gswm_extract_allreduce: the collective that follows K3, inside K3 ------------------------------------------------
+  // The last CTA to retire holds this rank's final counters; its first warp publishes them to every peer's mailbox over
+  // NVLink and collects the peers' (gswm_comm.cuh).  The other CTAs are gone by then: the wait costs one warp of one SM.
+  if (a.reduced != nullptr && threadIdx.x < 32) {
+    unsigned ticket = 0;
+    if (threadIdx.x == 0) {
+      __threadfence();                                                 // this CTA's counter atomics before its ticket
+      ticket = atomicAdd(a.comm.ticket, 1u);
+    }
+    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      long long mine[GSWM_COMM_MAX_VALUES], sum[GSWM_COMM_MAX_VALUES];
+      const long long own = threadIdx.x < GSWM_N_COUNTERS ? (long long)atomicAdd(&a.counters[threadIdx.x], 0ull) : 0ll;
+#pragma unroll
+      for (int i = 0; i < GSWM_COMM_MAX_VALUES; ++i) mine[i] = __shfl_sync(0xFFFFFFFFu, own, i);
+      comm_allreduce_warp(a.comm, mine, GSWM_N_COUNTERS, sum);
+#pragma unroll
+      for (int i = 0; i < GSWM_N_COUNTERS; ++i)
+        if (threadIdx.x == i) a.reduced[i] = sum[i];
+      if (threadIdx.x == 0) *a.comm.ticket = 0u;                       // ready for the next launch (stream-ordered)
+    }
+  }
+}
+
+// Stand-alone form of the same exchange (gswm_comm_allreduce_counters): one warp, in place.
+__global__ void __launch_bounds__(32)
+comm_allreduce_kernel(const CommDev c, long long* __restrict__ values, int n) {
+  long long mine[GSWM_COMM_MAX_VALUES], sum[GSWM_COMM_MAX_VALUES];
+#pragma unroll
+  for (int i = 0; i < GSWM_COMM_MAX_VALUES; ++i) mine[i] = i < n ? values[i] : 0ll;
+  comm_allreduce_warp(c, mine, n, sum);
+#pragma unroll
+  for (int i = 0; i < GSWM_COMM_MAX_VALUES; ++i)
+    if ((int)threadIdx.x == i && i < n) values[i] = sum[i];
 }
 
 // Test hook: evaluate the fp32 bucket quantile on caller-supplied raw words (exhaustive accuracy test).
@@ -719,6 +792,25 @@ debug_quantile_kernel(const uint32_t* __restrict__ w, int64_t n, uint32_t bucket
   *reinterpret_cast<float4*>(out + i) = z;
 }
 
+// Test hook: |z| of the refined outermost cell for caller-supplied 32-bit refinement words.
+__global__ void __launch_bounds__(kThreads)
+debug_top_cell_kernel(const uint32_t* __restrict__ w, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < n) out[i] = top_cell_quantile(w[i]);
+}
+
+// Test hook: the Philox4x32 core on caller-supplied counters / keys, 7 rounds (the product) or 10 (the variant with
+// published known-answer vectors).
+template <int kRounds>
+__global__ void __launch_bounds__(kThreads)
+debug_philox_kernel(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* p = in + 6 * i;
+  const uint4 r = philox4x32<kRounds>(make_uint4(p[0], p[1], p[2], p[3]), p[4], p[5]);
+  out[4 * i + 0] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
 __global__ void __launch_bounds__(kThreads)
 debug_ppf64_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -728,14 +820,22 @@ debug_ppf64_kernel(const double* __restrict__ p, int64_t n, double* __restrict__
 // ------------------------------------------------------------------------------------------------
 // host side of the device entry points
 // ------------------------------------------------------------------------------------------------
-static int check_job(const gswm_job* job, bool for_extract) {
+static inline bool per_latent_of(const gswm_job* job) { return (job->flags & GSWM_JOB_PER_LATENT) != 0; }
+
+int check_job(const gswm_job* job, bool for_extract) {
   if (!job || !job->d_keys || !job->d_nonces) return GSWM_E_NULL;
   if (!for_extract && !job->d_msgs) return GSWM_E_NULL;
-  if ((reinterpret_cast<uintptr_t>(job->d_keys) | reinterpret_cast<uintptr_t>(job->d_nonces) |
-       reinterpret_cast<uintptr_t>(job->d_msgs)) & 3u) return GSWM_E_ALIGN;   // read as 32-bit words
+  if ((reinterpret_cast<uintptr_t>(job->d_keys) | reinterpret_cast<uintptr_t>(job->d_nonces)) & 3u) return GSWM_E_ALIGN;   // read as 32-bit words
   if (job->n_latents < 0 || job->n_elems <= 0 || (job->n_elems % 4) != 0) return GSWM_E_SHAPE;
-  if (job->msg_bits <= 0 || (job->msg_bits % 32) != 0 || job->msg_bits > job->n_elems) return GSWM_E_MSGLEN;
-  if (for_extract && (job->n_elems % job->msg_bits) != 0) return GSWM_E_MSGLEN;
+  if (job->msg_bits <= 0 || job->msg_bits > job->n_elems) return GSWM_E_MSGLEN;
+  if (for_extract) {
+    // extract.py:91-98 splits the bit string into message_length-sized segments: any divisor of the latent size works
+    if ((job->n_elems % job->msg_bits) != 0) return GSWM_E_MSGLEN;
+  } else if ((job->msg_bits % 32) != 0) {
+    return GSWM_E_MSGLEN;
+  }
+  // message rows are read as 32-bit words whenever they are whole words (always for embed)
+  if ((job->msg_bits % 32) == 0 && (reinterpret_cast<uintptr_t>(job->d_msgs) & 3u)) return GSWM_E_ALIGN;
   if (job->n_elems > ((int64_t)1 << 31)) return GSWM_E_RANGE;
   const int64_t tiles = (job->n_elems + kTileElems - 1) / kTileElems;
   if (job->n_latents > 0x7FFFFFFFll || tiles > 32767) return GSWM_E_RANGE;    // grid.y carries tiles or half tiles
@@ -759,6 +859,7 @@ static EmbedArgs make_embed_args(const gswm_job* job) {
   a.msg_words = (uint32_t)job->msg_bits / 32;
   a.tiled_words = (uint32_t)(job->n_elems / job->msg_bits) * a.msg_words;
   a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
+  a.keys_in_flight = (job->flags & GSWM_JOB_KEYS_IN_FLIGHT) ? 1u : 0u;
   return a;
 }
 
@@ -855,11 +956,11 @@ const char* gswm_strerror(int code) {
     case GSWM_OK: return "success";
     case GSWM_E_NULL: return "gswm: a required pointer is NULL";
     case GSWM_E_SHAPE: return "gswm: n_elems must be a positive multiple of 4 and n_latents >= 0";
-    case GSWM_E_MSGLEN: return "gswm: msg_bits must be a positive multiple of 32, <= n_elems (and divide it for extract)";
+    case GSWM_E_MSGLEN: return "gswm: msg_bits must be positive and <= n_elems; a multiple of 32 for embed, a divisor of n_elems for extract";
     case GSWM_E_DTYPE: return "gswm: unknown element type";
     case GSWM_E_RANGE: return "gswm: size out of range";
-    case GSWM_E_WORKSPACE: return "gswm: workspace too small (reserved; no current entry point returns it)";
-    case GSWM_E_ALIGN: return "gswm: device pointer not 16-byte aligned";
+    case GSWM_E_COMM: return "gswm: communicator error (bad rank / size, peer memory not mappable, NCCL not loadable, or a peer timed out)";
+    case GSWM_E_ALIGN: return "gswm: latent pointer or row not 16-byte aligned, or key / nonce / message pointer not 4-byte aligned";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gswm: unknown error";
   }
 }
@@ -885,6 +986,27 @@ int gswm_debug_norm_ppf(const double* d_p, int64_t n, double* d_out, void* strea
   return (int)cudaGetLastError();
 }
 
+int gswm_debug_top_cell(const uint32_t* d_words, int64_t n, float* d_out, void* stream) {
+  if (!d_words || !d_out) return GSWM_E_NULL;
+  if (n < 0) return GSWM_E_SHAPE;
+  if (n == 0) return GSWM_OK;
+  debug_top_cell_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(d_words, n, d_out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int gswm_debug_philox4x32(const uint32_t* d_in, int64_t n, int32_t rounds, uint32_t* d_out, void* stream) {
+  if (!d_in || !d_out) return GSWM_E_NULL;
+  if (n < 0) return GSWM_E_SHAPE;
+  if (rounds != 7 && rounds != 10) return GSWM_E_RANGE;
+  if (n == 0) return GSWM_OK;
+  const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+  if (rounds == 7) debug_philox_kernel<7><<<grid, kThreads, 0, (cudaStream_t)stream>>>(d_in, n, d_out);
+  else debug_philox_kernel<10><<<grid, kThreads, 0, (cudaStream_t)stream>>>(d_in, n, d_out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
 int64_t gswm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int gswm_philox_rounds(void) { return GSWM_PHILOX_ROUNDS; }
@@ -898,11 +1020,6 @@ int gswm_debug_trace_select(int buf, void* stream) {                 // stream-o
   return (int)cudaMemcpyToSymbolAsync(g_trace_buf, &b, sizeof(b), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream);
 }
 #endif
-
-size_t gswm_workspace_bytes(const gswm_job* job) {
-  (void)job;                                                          // no entry point needs scratch memory any more
-  return 0;
-}
 
 int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int64_t n_streams,
                             int64_t n_bytes_each, uint8_t* d_out, void* stream) {
@@ -921,13 +1038,12 @@ int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int6
   return (int)cudaGetLastError();
 }
 
-int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent, float* d_out,
-               void* d_workspace, void* stream) {
+int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent, float* d_out, void* stream) {
   int rc = check_job(job, false);
   if (rc) return rc;
   if (!d_out) return GSWM_E_NULL;
   if (!aligned16(d_out)) return GSWM_E_ALIGN;
-  if (offset >> 62) return GSWM_E_RANGE;
+  if ((offset >> 62) || first_latent < 0) return GSWM_E_RANGE;        // a negative index would wrap into another latent's counters
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   EmbedArgs a = make_embed_args(job);
@@ -939,15 +1055,14 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
     a.rk.k[2 * r] = a.seed_lo + (uint32_t)r * 0x9E3779B9u;
     a.rk.k[2 * r + 1] = a.seed_hi + (uint32_t)r * 0xBB67AE85u;
   }
-  (void)d_workspace;                                                  // reserved (see gswm_workspace_bytes)
-  rc = job->per_latent ? launch_embed(embed_kernel<true>, a, a.tiles_per_latent, false, st)
-                       : launch_embed(embed_kernel<false>, a, halves_of(job->n_elems), true, st);   // Y = non-empty half tiles
+  rc = per_latent_of(job) ? launch_embed(embed_kernel<true>, a, a.tiles_per_latent, false, st)
+                          : launch_embed(embed_kernel<false>, a, halves_of(job->n_elems), true, st);   // Y = non-empty half tiles
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return rc;
 }
 
 int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_latent, void* d_out,
-                        int32_t out_dtype, void* d_workspace, void* stream) {
+                        int32_t out_dtype, void* stream) {
   int rc = check_job(job, false);
   if (rc) return rc;
   if (!d_out || !d_u) return GSWM_E_NULL;
@@ -955,57 +1070,86 @@ int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_la
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   EmbedArgs a = make_embed_args(job);
-  (void)d_workspace;                                                  // not needed by this entry point
   const dim3 grid((unsigned)job->n_latents, tiles_of(job->n_elems));
   const int upl = u_per_latent ? 1 : 0;
   if (out_dtype == GSWM_F32) {
-    if (job->per_latent) embed_injected_kernel<true, float><<<grid, kThreads, 0, st>>>(a, d_u, upl, (float*)d_out);
+    if (per_latent_of(job)) embed_injected_kernel<true, float><<<grid, kThreads, 0, st>>>(a, d_u, upl, (float*)d_out);
     else embed_injected_kernel<false, float><<<grid, kThreads, 0, st>>>(a, d_u, upl, (float*)d_out);
   } else {
-    if (job->per_latent) embed_injected_kernel<true, double><<<grid, kThreads, 0, st>>>(a, d_u, upl, (double*)d_out);
+    if (per_latent_of(job)) embed_injected_kernel<true, double><<<grid, kThreads, 0, st>>>(a, d_u, upl, (double*)d_out);
     else embed_injected_kernel<false, double><<<grid, kThreads, 0, st>>>(a, d_u, upl, (double*)d_out);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
 
-int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t* d_msg_out, uint16_t* d_counts,
-                 int32_t* d_matched, int64_t* d_counters, void* d_workspace, void* stream) {
+}  // extern "C"
+
+namespace gswm {
+// gswm_extract and gswm_extract_allreduce (the latter from gswm_comm.cu, which owns the communicator)
+int extract_impl(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t* d_msg_out, uint16_t* d_counts,
+                 int32_t* d_matched, uint8_t* d_flags, int64_t* d_counters, const CommDev* comm, int64_t* d_reduced,
+                 void* stream) {
   int rc = check_job(job, true);
   if (rc) return rc;
   if (!d_z || !d_msg_out) return GSWM_E_NULL;
   if (z_dtype != GSWM_F32 && z_dtype != GSWM_F16 && z_dtype != GSWM_BF16 && z_dtype != GSWM_F64) return GSWM_E_DTYPE;
-  if (!aligned16(d_z) || (reinterpret_cast<uintptr_t>(d_msg_out) & 3u)) return GSWM_E_ALIGN;
+  const bool whole_words = (job->msg_bits % 32) == 0;
+  if (!aligned16(d_z) || (whole_words && (reinterpret_cast<uintptr_t>(d_msg_out) & 3u))) return GSWM_E_ALIGN;
+  const size_t esz = z_dtype == GSWM_F32 ? 4 : z_dtype == GSWM_F64 ? 8 : 2;
+  if (((size_t)job->n_elems * esz) % 16 != 0) return GSWM_E_ALIGN;     // every latent row is fetched with 16-byte bulk copies
   const int64_t copies = job->n_elems / job->msg_bits;
   if (d_counts && copies > 65535) return GSWM_E_RANGE;
   if (job->msg_bits > 8192) return GSWM_E_RANGE;
-  if (job->n_latents == 0) return GSWM_OK;
+  if (comm && (!d_reduced || !d_counters)) return GSWM_E_NULL;
+  if (job->n_latents == 0 && !comm) return GSWM_OK;
+  if (job->n_latents == 0) return GSWM_E_SHAPE;                        // the fused exchange lives in the extract kernel: it needs one launch
   cudaStream_t st = (cudaStream_t)stream;
   ExtractArgs a{};
-  (void)d_workspace;                                                  // not needed by this entry point
+  const bool per_latent = per_latent_of(job);
   a.keys = job->d_keys; a.nonces = job->d_nonces; a.msgs = job->d_msgs;
-  a.z = d_z; a.msg_out = d_msg_out; a.counts = d_counts; a.matched = d_matched;
+  a.z = d_z; a.msg_out = d_msg_out; a.counts = d_counts; a.matched = d_matched; a.flags = d_flags;
   a.counters = reinterpret_cast<unsigned long long*>(d_counters);
   a.n_elems = job->n_elems;
   a.tiles_per_latent = tiles_of(job->n_elems);
   a.msg_bits = (uint32_t)job->msg_bits;
-  a.msg_stride_bytes = (uint32_t)job->msg_bits / 8;
+  a.msg_stride_bytes = ((uint32_t)job->msg_bits + 7u) / 8u;
   a.copies = (uint32_t)copies;
   a.n_latents = job->n_latents;
+  a.keys_in_flight = (job->flags & GSWM_JOB_KEYS_IN_FLIGHT) ? 1u : 0u;
+  if (comm) {
+    a.comm = *comm;
+    a.reduced = reinterpret_cast<long long*>(d_reduced);
+  }
   const int64_t chunk_elems = z_dtype == GSWM_F32 ? Chunk<float>::kElems : z_dtype == GSWM_F64 ? Chunk<double>::kElems : Chunk<__half>::kElems;
   a.chunks_per_latent = (uint32_t)((job->n_elems + chunk_elems - 1) / chunk_elems);
-  const bool pow2 = (1024 % job->msg_bits) == 0;
-  a.ks_cache_tiles = (!job->per_latent && a.tiles_per_latent <= 8) ? a.tiles_per_latent : 0;
+  // fast path: a thread's four vote positions never change (msg_bits is a power of two in [4, 1024]); otherwise shared-memory atomics
+  const bool pow2 = job->msg_bits >= 4 && (1024 % job->msg_bits) == 0;
+  a.ks_cache_tiles = (!per_latent && a.tiles_per_latent <= 8) ? a.tiles_per_latent : 0;
   const int stages = z_dtype != GSWM_F32 ? Ring<__half, false>::kStages
-                                         : (job->per_latent ? Ring<float, true>::kStages : Ring<float, false>::kStages);
+                                         : (per_latent ? Ring<float, true>::kStages : Ring<float, false>::kStages);
   const size_t smem = (size_t)stages * kStageBytes +
                       (size_t)((a.ks_cache_tiles ? a.ks_cache_tiles : 1u) * kTileWords + job->msg_bits) * sizeof(uint32_t);
-  if (z_dtype == GSWM_F32) rc = launch_extract<float>(a, job->per_latent != 0, pow2, smem, st);
-  else if (z_dtype == GSWM_F64) rc = launch_extract<double>(a, job->per_latent != 0, pow2, smem, st);
-  else if (z_dtype == GSWM_F16) rc = launch_extract<__half>(a, job->per_latent != 0, pow2, smem, st);
-  else rc = launch_extract<__nv_bfloat16>(a, job->per_latent != 0, pow2, smem, st);
+  if (z_dtype == GSWM_F32) rc = launch_extract<float>(a, per_latent, pow2, smem, st);
+  else if (z_dtype == GSWM_F64) rc = launch_extract<double>(a, per_latent, pow2, smem, st);
+  else if (z_dtype == GSWM_F16) rc = launch_extract<__half>(a, per_latent, pow2, smem, st);
+  else rc = launch_extract<__nv_bfloat16>(a, per_latent, pow2, smem, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return rc;
+}
+
+int comm_allreduce_launch(const CommDev& c, int64_t* d_values, int n, void* stream) {
+  comm_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c, reinterpret_cast<long long*>(d_values), n);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+}  // namespace gswm
+
+extern "C" {
+
+int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t* d_msg_out, uint16_t* d_counts,
+                 int32_t* d_matched, uint8_t* d_flags, int64_t* d_counters, void* stream) {
+  return gswm::extract_impl(job, d_z, z_dtype, d_msg_out, d_counts, d_matched, d_flags, d_counters, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -103,7 +103,7 @@ __device__ __forceinline__ uint4 philox4x32_keys(uint4 c, const PhiloxKeys& rk) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// The product's uniform source ("gswm uniforms v2", restated in oracle/gs_oracle.py:gswm_uniform_grid).
+// The product's uniform source ("gswm uniforms v3", restated in oracle/gs_oracle.py:gswm_uniforms).
 //
 // Every element gets a 23-bit integer m; its uniform is
 //       u = v        if the element's bucket bit y is 1,        v = (m + 1/2) 2^-23
@@ -117,6 +117,13 @@ __device__ __forceinline__ uint4 philox4x32_keys(uint4 c, const PhiloxKeys& rk) 
 // The m's come from Philox in groups: three Philox4x32 calls (384 bits) feed 16 elements -- the four
 // float4 a thread stores in one "super-iteration".  float4 k = 0..2 take the top 23 bits of call k's
 // four words; float4 3 is assembled from the otherwise unused low bytes of the three calls.
+//
+// v3: the outermost cell m = 2^23 - 1 (v in [1 - 2^-23, 1): probability 2^-23 per element, |z| >= 5.3) is SUBDIVIDED
+// instead of being represented by its midpoint: a fourth Philox call (counter word 3 = call index 3, key word 1 + k
+// for float4 k) yields a 28-bit m2 and v = 1 - (m2 + 1/2) 2^-51, so that the watermarked noise has the reference's
+// support -- |z| up to 8.2095 = norm.ppf(1 - 2^-53), the largest value gs_insert.py:62-64 can produce for bucket
+// bit 1 -- where the plain 23-bit grid stops at 5.42 (tail mass 6e-8 cut off).  The refinement lives in the rare tail
+// block and is evaluated in float64 (top_cell_quantile below); the hot path is unchanged.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t r;
@@ -162,7 +169,7 @@ __device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT
   return r;
 }
 
-__device__ __forceinline__ float quantile_tail(float x) {           // x < XSPLIT, ~0.12 % of elements
+__device__ __forceinline__ float quantile_tail(float x) {           // m > M_SPLIT, ~0.12 % of elements
   return horner_tail(sqrt_fast(GSWM_HNQ_CSHIFT - x) - GSWM_HNQ_S0);
 }
 
@@ -218,14 +225,61 @@ __device__ __forceinline__ void quantile_front1(uint32_t fa, float& v, float& x)
 #define GSWM_QUANTILE_MODE 0      // 0: both pairs packed (FFMA2); 1: pair 0 packed, pair 1 scalar; 2: all scalar
 #endif
 
+// The outermost grid cell, refined (uniforms v3).  w: 32 fresh Philox bits; m2 = w >> 4 (28 bits);
+// p = P(|Z| > z) / 2 = (m2 + 1/2) 2^-52;  |z| = -Phi^-1(p) = R(sqrt(52 - lg2(m2 + 1/2)) - S1), R of degree 5 fitted like the
+// others (tools/fit_halfnormal_quantile.py: 1.9e-7 relative in emulated fp32), |z| in [5.29, 8.21].  Reached about once
+// per 8 M elements, from inside the rare tail block: ~15 instructions plus one Philox call there, nothing anywhere else.
+__device__ __forceinline__ float top_cell_quantile(uint32_t w) {
+  const float c[] = {GSWM_HNQ_FARTAIL_COEFFS};
+  const float mf = (float)(w >> 4) + 0.5f;
+  const float s = sqrt_fast(52.0f - lg2_fast(mf)) - GSWM_HNQ_S1;
+  float p = c[0];
+#pragma unroll
+  for (int i = 1; i < (int)(sizeof(c) / sizeof(float)); ++i) p = fmaf(p, s, c[i]);
+  return p;
+}
+struct NoTopCell {                                                   // test hook / callers without a counter: the cell's midpoint
+  __device__ __forceinline__ float operator()(uint32_t, float x) const { return quantile_tail(x); }
+};
+// Element j of float4 k of the super-iteration whose Philox counter is g_base + g_add (words 0..1), (off_lo, off_hi)
+// (words 2..3 of call 0): the refinement bits are word j of Philox call 3 of that counter under key (seed_lo, seed_hi + k).
+struct TopCellRefine {
+  uint64_t g_base;          // loop-carried counter of the caller (live across the loop whatever happens here)
+  uint32_t g_add;
+  uint32_t off_lo, off_hi, seed_lo, seed_hi, k;
+  __device__ __forceinline__ float operator()(uint32_t j, float) const {
+    uint64_t gb = g_base;
+    asm volatile("" : "+l"(gb));      // opaque copy: the counter is re-derived HERE, in the rare block, instead of being kept
+                                      // alive (two registers) across the whole super-iteration for it
+    const uint64_t g = gb + g_add;
+    const uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), off_lo, off_hi + 3u), seed_lo, seed_hi + k);
+    return top_cell_quantile(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
+  }
+};
+constexpr float kTopCellX = -18.5f;
+
+#ifndef GSWM_TAIL_INT
+#define GSWM_TAIL_INT 1           // 1: central / tail decided on the integer f bits (before the MUFU); 0: on x (round-1 form)
+#endif
+
 // |z| of four elements from their f bit patterns; `sgn` (+-1 per element: +1 for bucket bit 1) gives z.
 // kWarpUniformTail (callers whose whole warp is converged here): the rare tail patch is entered on a warp VOTE, i.e.
 // through a uniform branch -- the warp executes the patch block when any lane needs it either way, but a uniform branch
 // needs no reconvergence barrier (BSSY / BSYNC) around the common fall-through: 56.3 -> 55.3 us per 4096 SD-2.1 latents,
 // bit-identical output.
-template <bool kWarpUniformTail = false>
-__device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, float4 sgn) {
+// WHETHER the patch block is entered is decided on the integers: x < XSPLIT implies bits(f) > GSWM_HNQ_FGUARD_BITS (x is
+// monotone in m up to rounding steps; the guard sits 64 grid points below the split, tools/fit_halfnormal_quantile.py
+// checks the implication over all 2^23 m) -- one three-input integer maximum and two compares on values that exist
+// before the MUFU.LG2 is even issued, instead of a float minimum tree behind it.  WHICH formula an element gets is its
+// own x < XSPLIT, as before.
+template <bool kWarpUniformTail = false, typename TopCell = NoTopCell>
+__device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, float4 sgn,
+                                                       const TopCell top = TopCell()) {
   float2 v01, v23, x01, x23, g01, g23;
+#if GSWM_TAIL_INT && !defined(GSWM_WHATIF_NOTAIL)
+  bool any_tail = __vimax3_u32(f0, f1, f2) > GSWM_HNQ_FGUARD_BITS || f3 > GSWM_HNQ_FGUARD_BITS;
+  if (kWarpUniformTail) any_tail = __any_sync(0xFFFFFFFFu, any_tail);
+#endif
 #if GSWM_QUANTILE_MODE == 2
   quantile_front1(f0, v01.x, x01.x);
   quantile_front1(f1, v01.y, x01.y);
@@ -243,13 +297,17 @@ __device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1,
   g23 = __fmul2_rn(v23, horner_central2(x23));
 #endif
 #ifndef GSWM_WHATIF_NOTAIL
+#if !GSWM_TAIL_INT
   bool any_tail = fminf(fminf(x01.x, x01.y), fminf(x23.x, x23.y)) < GSWM_HNQ_XSPLIT;
   if (kWarpUniformTail) any_tail = __any_sync(0xFFFFFFFFu, any_tail);
+#endif
   if (any_tail) {
-    if (x01.x < GSWM_HNQ_XSPLIT) g01.x = quantile_tail(x01.x);
-    if (x01.y < GSWM_HNQ_XSPLIT) g01.y = quantile_tail(x01.y);
-    if (x23.x < GSWM_HNQ_XSPLIT) g23.x = quantile_tail(x23.x);
-    if (x23.y < GSWM_HNQ_XSPLIT) g23.y = quantile_tail(x23.y);
+    // per element the decision is its own x (the f bit patterns are dead by now: nothing is kept alive across the Horner
+    // chains for this block); the outermost cell is x < -18.5 (m = 2^23 - 1: x = -19.0; m = 2^23 - 2: x = -17.4)
+    if (x01.x < GSWM_HNQ_XSPLIT) g01.x = x01.x < kTopCellX ? top(0, x01.x) : quantile_tail(x01.x);
+    if (x01.y < GSWM_HNQ_XSPLIT) g01.y = x01.y < kTopCellX ? top(1, x01.y) : quantile_tail(x01.y);
+    if (x23.x < GSWM_HNQ_XSPLIT) g23.x = x23.x < kTopCellX ? top(2, x23.x) : quantile_tail(x23.x);
+    if (x23.y < GSWM_HNQ_XSPLIT) g23.y = x23.y < kTopCellX ? top(3, x23.y) : quantile_tail(x23.y);
   }
 #endif
 #ifdef GSWM_WHATIF_NOSIGN
@@ -268,45 +326,6 @@ __device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1,
 #endif
 }
 
-// Eight elements (two float4) at once: four independent packed Horner chains in one basic block, and ONE
-// compare-and-branch for the rare tail patch -- the branch is a scheduling barrier, so halving their number both
-// saves issue slots and lets the four chains hide each other's FFMA latency.
-__device__ __forceinline__ void bucket_quantile8_f32(const uint32_t (&fa)[4], const uint32_t (&fb)[4], float4 sa, float4 sb,
-                                                     float4& za, float4& zb) {
-  float2 v0, v1, v2, v3, x0, x1, x2, x3;
-  quantile_front2(fa[0], fa[1], v0, x0);
-  quantile_front2(fa[2], fa[3], v1, x1);
-  quantile_front2(fb[0], fb[1], v2, x2);
-  quantile_front2(fb[2], fb[3], v3, x3);
-  const float c[] = {GSWM_HNQ_CENTRAL_COEFFS};
-  float2 p0 = splat2(c[0]), p1 = p0, p2 = p0, p3 = p0;
-#pragma unroll
-  for (int i = 1; i < (int)(sizeof(c) / sizeof(float)); ++i) {
-    p0 = __ffma2_rn(p0, x0, splat2(c[i]));
-    p1 = __ffma2_rn(p1, x1, splat2(c[i]));
-    p2 = __ffma2_rn(p2, x2, splat2(c[i]));
-    p3 = __ffma2_rn(p3, x3, splat2(c[i]));
-  }
-  float2 g0 = __fmul2_rn(v0, p0), g1 = __fmul2_rn(v1, p1), g2 = __fmul2_rn(v2, p2), g3 = __fmul2_rn(v3, p3);
-  const float lo = fminf(fminf(fminf(x0.x, x0.y), fminf(x1.x, x1.y)), fminf(fminf(x2.x, x2.y), fminf(x3.x, x3.y)));
-  if (lo < GSWM_HNQ_XSPLIT) {
-    if (x0.x < GSWM_HNQ_XSPLIT) g0.x = quantile_tail(x0.x);
-    if (x0.y < GSWM_HNQ_XSPLIT) g0.y = quantile_tail(x0.y);
-    if (x1.x < GSWM_HNQ_XSPLIT) g1.x = quantile_tail(x1.x);
-    if (x1.y < GSWM_HNQ_XSPLIT) g1.y = quantile_tail(x1.y);
-    if (x2.x < GSWM_HNQ_XSPLIT) g2.x = quantile_tail(x2.x);
-    if (x2.y < GSWM_HNQ_XSPLIT) g2.y = quantile_tail(x2.y);
-    if (x3.x < GSWM_HNQ_XSPLIT) g3.x = quantile_tail(x3.x);
-    if (x3.y < GSWM_HNQ_XSPLIT) g3.y = quantile_tail(x3.y);
-  }
-  g0 = __fmul2_rn(g0, make_float2(sa.x, sa.y));
-  g1 = __fmul2_rn(g1, make_float2(sa.z, sa.w));
-  g2 = __fmul2_rn(g2, make_float2(sb.x, sb.y));
-  g3 = __fmul2_rn(g3, make_float2(sb.z, sb.w));
-  za = make_float4(g0.x, g0.y, g1.x, g1.y);
-  zb = make_float4(g2.x, g2.y, g3.x, g3.y);
-}
-
 // ------------------------------------------------------------------------------------------------
 // fp64 path (injected uniforms): z = Phi^-1(p), p = (u + y) / 2 computed exactly as the reference
 // does.  Same structure, natural log, degree-14 polynomials; relative error ~1e-12.
@@ -319,7 +338,7 @@ __device__ __forceinline__ double horner64(const double (&c)[N], double x) {
   return p;
 }
 
-__device__ __forceinline__ double norm_ppf_f64(double p) {
+__device__ inline double norm_ppf_f64(double p) {
   // t = 2 min(p, 1-p) in (0,1]; both branches are exact in binary64 for p in [0,1]
   const bool upper = p > 0.5;
   const double t = upper ? 2.0 - 2.0 * p : 2.0 * p;

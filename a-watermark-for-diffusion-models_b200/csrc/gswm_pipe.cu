@@ -37,6 +37,7 @@ struct Slot {
   uint8_t* h_msg_out = nullptr;   // chunk * kMaxMsgBytes
   uint16_t* h_counts = nullptr;   // chunk * 8192
   int32_t* h_matched = nullptr;   // chunk
+  uint8_t* h_flags = nullptr;     // chunk
   // what the staging currently holds (to be delivered to the caller), -1 = nothing
   int64_t pending_first = -1, pending_n = 0;
 };
@@ -75,10 +76,14 @@ int check_host_job(const gswm_pipe* p, const gswm_host_job* j, bool need_msg) {
   if (need_msg && !j->h_msgs) return GSWM_E_NULL;
   if (j->n_latents < 0 || j->n_elems <= 0 || (j->n_elems % 4) != 0) return GSWM_E_SHAPE;
   if (j->n_elems > p->max_elems) return GSWM_E_RANGE;
-  if (j->msg_bits <= 0 || (j->msg_bits % 32) != 0 || j->msg_bits > j->n_elems) return GSWM_E_MSGLEN;
+  if (j->msg_bits <= 0 || j->msg_bits > j->n_elems) return GSWM_E_MSGLEN;
+  if (need_msg && (j->msg_bits % 32) != 0) return GSWM_E_MSGLEN;      // embed (gswm_job rules); extract takes any divisor
   if (j->msg_bits > kMaxMsgBytes * 8) return GSWM_E_RANGE;
   return GSWM_OK;
 }
+
+inline int64_t msg_row_bytes(const gswm_host_job* j) { return (j->msg_bits + 7) / 8; }
+inline bool host_per_latent(const gswm_host_job* j) { return (j->flags & GSWM_JOB_PER_LATENT) != 0; }
 
 struct DeviceKeys {
   const uint8_t* keys;
@@ -90,9 +95,9 @@ struct DeviceKeys {
 // Upload the whole call's key material once (pinned staging -> device, on slot 0's stream; the other slots
 // wait for it through an event).
 int upload_keys(gswm_pipe* p, const gswm_host_job* hj, DeviceKeys* dk) {
-  const int64_t rows = hj->per_latent ? hj->n_latents : 1;
-  const int64_t mb = hj->msg_bits / 8;
-  const size_t need = (size_t)rows * (32 + 16 + (hj->h_msgs ? mb : 0));
+  const int64_t rows = host_per_latent(hj) ? hj->n_latents : 1;
+  const int64_t mb = msg_row_bytes(hj);
+  const size_t need = (size_t)rows * (32 + 16 + (hj->h_msgs ? mb : 0));   // [keys | nonces | msgs]: msgs start 4-byte aligned (48 rows)
   if (need > p->km_capacity) {
     if (p->d_km) cudaFree(p->d_km);
     if (p->h_km) cudaFreeHost(p->h_km);
@@ -119,11 +124,11 @@ int upload_keys(gswm_pipe* p, const gswm_host_job* hj, DeviceKeys* dk) {
 }
 
 void chunk_job(const gswm_host_job* hj, const DeviceKeys& dk, int64_t first, int64_t n, gswm_job* dj) {
-  const int64_t row0 = hj->per_latent ? first : 0;
+  const int64_t row0 = host_per_latent(hj) ? first : 0;
   dj->n_latents = n;
   dj->n_elems = hj->n_elems;
   dj->msg_bits = hj->msg_bits;
-  dj->per_latent = hj->per_latent;
+  dj->flags = hj->flags & GSWM_JOB_PER_LATENT;
   dj->d_keys = dk.keys + row0 * 32;
   dj->d_nonces = dk.nonces + row0 * 16;
   dj->d_msgs = dk.msgs ? dk.msgs + row0 * dk.msg_bytes : nullptr;
@@ -138,13 +143,15 @@ int sync_all(gswm_pipe* p, int rc) {
 }
 
 // Deliver what a slot's pinned staging holds to the caller's arrays (after the slot's last copy finished).
-int drain_slot(Slot& s, int64_t msg_bytes, int64_t msg_bits, uint8_t* h_msg_out, uint16_t* h_counts, int32_t* h_matched) {
+int drain_slot(Slot& s, int64_t msg_bytes, int64_t msg_bits, uint8_t* h_msg_out, uint16_t* h_counts, int32_t* h_matched,
+               uint8_t* h_flags) {
   if (s.pending_first < 0) return GSWM_OK;
   GSWM_CUDA(cudaEventSynchronize(s.done));
   const int64_t f = s.pending_first, n = s.pending_n;
   std::memcpy(h_msg_out + f * msg_bytes, s.h_msg_out, (size_t)(n * msg_bytes));
   if (h_counts) std::memcpy(h_counts + f * msg_bits, s.h_counts, (size_t)(n * msg_bits) * sizeof(uint16_t));
   if (h_matched) std::memcpy(h_matched + f, s.h_matched, (size_t)n * sizeof(int32_t));
+  if (h_flags) std::memcpy(h_flags + f, s.h_flags, (size_t)n);
   s.pending_first = -1;
   return GSWM_OK;
 }
@@ -179,6 +186,7 @@ int gswm_pipe_create(gswm_pipe** out, int device, int64_t max_elems, int64_t max
     H((void**)&s.h_msg_out, (size_t)p->chunk * kMaxMsgBytes);
     H((void**)&s.h_counts, (size_t)p->chunk * 8192 * sizeof(uint16_t));
     H((void**)&s.h_matched, (size_t)p->chunk * sizeof(int32_t));
+    H((void**)&s.h_flags, (size_t)p->chunk);
   }
   A((void**)&p->d_counters, GSWM_N_COUNTERS * sizeof(int64_t));
   H((void**)&p->h_counters, GSWM_N_COUNTERS * sizeof(int64_t));
@@ -196,7 +204,7 @@ void gswm_pipe_destroy(gswm_pipe* p) {
   for (auto& s : p->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_in); cudaFree(s.d_out);
-    cudaFreeHost(s.h_msg_out); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_matched);
+    cudaFreeHost(s.h_msg_out); cudaFreeHost(s.h_counts); cudaFreeHost(s.h_matched); cudaFreeHost(s.h_flags);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
@@ -222,7 +230,7 @@ int gswm_pipe_embed(gswm_pipe* p, const gswm_host_job* job, uint64_t seed, uint6
     const int64_t n = std::min(p->chunk, job->n_latents - first);
     gswm_job dj;
     chunk_job(job, dk, first, n, &dj);
-    if ((rc = gswm_embed(&dj, seed, offset, first_latent + first, (float*)s.d_out, nullptr, s.stream))) break;
+    if ((rc = gswm_embed(&dj, seed, offset, first_latent + first, (float*)s.d_out, s.stream))) break;
     rc = (int)cudaMemcpyAsync(reinterpret_cast<char*>(h_out) + (size_t)first * row_bytes, s.d_out, (size_t)n * row_bytes,
                               cudaMemcpyDeviceToHost, s.stream);
   }
@@ -249,7 +257,7 @@ int gswm_pipe_embed_injected(gswm_pipe* p, const gswm_host_job* job, const doubl
     chunk_job(job, dk, first, n, &dj);
     const char* u_src = reinterpret_cast<const char*>(h_u) + (u_per_latent ? (size_t)first * u_row : 0);
     if ((rc = (int)cudaMemcpyAsync(s.d_in, u_src, (u_per_latent ? (size_t)n : 1) * u_row, cudaMemcpyHostToDevice, s.stream))) break;
-    if ((rc = gswm_embed_injected(&dj, (const double*)s.d_in, u_per_latent, s.d_out, out_dtype, nullptr, s.stream))) break;
+    if ((rc = gswm_embed_injected(&dj, (const double*)s.d_in, u_per_latent, s.d_out, out_dtype, s.stream))) break;
     rc = (int)cudaMemcpyAsync(reinterpret_cast<char*>(h_out) + (size_t)first * out_row, s.d_out, (size_t)n * out_row,
                               cudaMemcpyDeviceToHost, s.stream);
   }
@@ -257,7 +265,7 @@ int gswm_pipe_embed_injected(gswm_pipe* p, const gswm_host_job* job, const doubl
 }
 
 int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, int32_t z_dtype, uint8_t* h_msg_out,
-                      uint16_t* h_counts, int32_t* h_matched, int64_t* h_counters) {
+                      uint16_t* h_counts, int32_t* h_matched, uint8_t* h_flags, int64_t* h_counters) {
   int rc = check_host_job(p, job, false);
   if (rc) return rc;
   if (!h_z || !h_msg_out) return GSWM_E_NULL;
@@ -266,7 +274,7 @@ int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, i
   GSWM_CUDA(cudaSetDevice(p->device));
   const size_t esz = z_dtype == GSWM_F32 ? 4 : z_dtype == GSWM_F64 ? 8 : 2;
   const size_t z_row = (size_t)job->n_elems * esz;
-  const int64_t mb = job->msg_bits / 8;
+  const int64_t mb = msg_row_bytes(job);
   const bool want_matched = h_matched && job->h_msgs;
   // counters are accumulated by both slots' kernels: zero them (with the key upload) on slot 0's stream, which the
   // other slots wait for inside upload_keys
@@ -279,20 +287,20 @@ int gswm_pipe_extract(gswm_pipe* p, const gswm_host_job* job, const void* h_z, i
     Slot& s = p->slot[c % kSlots];
     const int64_t n = std::min(p->chunk, job->n_latents - first);
     // the slot's staging still holds the outputs of chunk c - kSlots: hand them to the caller first
-    if ((rc = drain_slot(s, mb, job->msg_bits, h_msg_out, h_counts, want_matched ? h_matched : nullptr))) break;
+    if ((rc = drain_slot(s, mb, job->msg_bits, h_msg_out, h_counts, want_matched ? h_matched : nullptr, h_flags))) break;
     gswm_job dj;
     chunk_job(job, dk, first, n, &dj);
     if ((rc = (int)cudaMemcpyAsync(s.d_in, reinterpret_cast<const char*>(h_z) + (size_t)first * z_row, (size_t)n * z_row,
                                    cudaMemcpyHostToDevice, s.stream))) break;
     // small outputs: the kernel stores them straight into the slot's mapped host staging (no copy-engine work)
     if ((rc = gswm_extract(&dj, s.d_in, z_dtype, s.h_msg_out, h_counts ? s.h_counts : nullptr,
-                           want_matched ? s.h_matched : nullptr, p->d_counters, nullptr, s.stream))) break;
+                           want_matched ? s.h_matched : nullptr, h_flags ? s.h_flags : nullptr, p->d_counters, s.stream))) break;
     if ((rc = (int)cudaEventRecord(s.done, s.stream))) break;
     s.pending_first = first;
     s.pending_n = n;
   }
   for (auto& s : p->slot) {
-    const int r2 = drain_slot(s, mb, job->msg_bits, h_msg_out, h_counts, want_matched ? h_matched : nullptr);
+    const int r2 = drain_slot(s, mb, job->msg_bits, h_msg_out, h_counts, want_matched ? h_matched : nullptr, h_flags);
     if (rc == 0) rc = r2;
   }
   if (rc == 0 && h_counters) {               // after every slot's kernels: slot 0 waits for the others, then publishes

@@ -11,11 +11,11 @@ every compute call needs a CUDA device and the built library.
 """
 from . import _lib
 from ._lib import GswmError, build, launch_count
-from .codec import (DEFAULT_KEY_HEX, DEFAULT_NONCE_HEX, ExtractResult, HostPipe, KeyMaterial, chacha20_keystream,
-                    choose_watermark_length, embed_batch, embed_batch_injected, embed_extract_batch, extract_batch,
-                    pad_message,
-                    resolve_key_nonce)
+from .codec import (DEFAULT_KEY_HEX, DEFAULT_NONCE_HEX, Comm, ExtractResult, HostPipe, KeyMaterial, chacha20_keystream,
+                    choose_watermark_length, embed_batch, embed_batch_injected, embed_batch_mt19937, embed_extract_batch,
+                    extract_batch, mt19937_uniform, pad_message, resolve_key_nonce)
 
-__all__ = ["GswmError", "build", "launch_count", "DEFAULT_KEY_HEX", "DEFAULT_NONCE_HEX", "ExtractResult", "HostPipe",
+__all__ = ["GswmError", "build", "launch_count", "DEFAULT_KEY_HEX", "DEFAULT_NONCE_HEX", "Comm", "ExtractResult", "HostPipe",
            "KeyMaterial", "chacha20_keystream", "choose_watermark_length", "embed_batch", "embed_batch_injected",
-           "embed_extract_batch", "extract_batch", "pad_message", "resolve_key_nonce", "_lib"]
+           "embed_batch_mt19937", "embed_extract_batch", "extract_batch", "mt19937_uniform", "pad_message",
+           "resolve_key_nonce", "_lib"]

@@ -20,6 +20,25 @@ def draw_uniforms(n: int, seeded: bool, seed: Optional[int], copies: int = 1) ->
     return np.random.uniform(0, 1, size=(copies, n)) if copies > 1 else np.random.uniform(0, 1, size=n)
 
 
+def seed_is_mt_int(seed) -> bool:
+    """True when ``RandomState(seed)`` takes numpy's integer path (init_genrand): the case the device generator restates."""
+    return isinstance(seed, (int, np.integer)) and not isinstance(seed, bool) and 0 <= int(seed) <= 0xFFFFFFFF
+
+
+def embed_seeded(seed, latent_shape: Sequence[int], key: bytes, nonce: bytes, k: bytes, msg_bits: int,
+                 out_dtype: torch.dtype, device=None) -> torch.Tensor:
+    """One latent whose uniforms are ``RandomState(seed).uniform(0, 1)`` per element (nodes.py:52-53,117; v1.5.2:27,75).
+    For an integer seed the whole thing runs on the GPU -- MT19937 stream, Phi^-1, scatter -- and nothing is uploaded;
+    any other seed numpy accepts (None, arrays) draws on the host like the reference and takes the injected path.
+    Returns a device tensor [1, *latent_shape]."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if seed_is_mt_int(seed):
+        km = codec.KeyMaterial.make(key, nonce, k, msg_bits)
+        return codec.embed_batch_mt19937(int(seed), 1, latent_shape, km, out_dtype, dev)
+    n = int(np.prod(latent_shape))
+    return embed_injected(draw_uniforms(n, True, seed), latent_shape, key, nonce, k, msg_bits, 1, out_dtype, dev)
+
+
 def embed_injected(u: np.ndarray, latent_shape: Sequence[int], key: bytes, nonce: bytes, k: bytes, msg_bits: int,
                    n_latents: int, out_dtype: torch.dtype, device=None) -> torch.Tensor:
     """z = norm.ppf((u + y) / 2) on the GPU in float64 for n_latents latents; returns a device tensor."""

@@ -92,11 +92,13 @@ class KeyMaterial:
 
     @classmethod
     def make(cls, key: BytesLike, nonce: BytesLike, msg: Optional[BytesLike], msg_bits: int) -> "KeyMaterial":
-        if msg_bits <= 0 or msg_bits % 32:
-            raise ValueError("message length must be a positive multiple of 32 bits")
+        """``msg_bits``: embedding needs a positive multiple of 32; extraction takes any positive length that divides
+        the latent (extract.py:195 ``--message_length`` is an arbitrary integer).  Message rows are (msg_bits + 7) // 8 bytes."""
+        if msg_bits <= 0:
+            raise ValueError("message length must be positive")
         k = _as_u8_rows(key, 32, "key")
         n = _as_u8_rows(nonce, 16, "nonce")
-        m = None if msg is None else _as_u8_rows(msg, msg_bits // 8, "message")
+        m = None if msg is None else _as_u8_rows(msg, (msg_bits + 7) // 8, "message")
         rows = {k.shape[0], n.shape[0]} | ({m.shape[0]} if m is not None else set())
         big = max(rows)
         if rows - {1, big}:
@@ -120,28 +122,45 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-class _DeviceJob:
-    """Key material uploaded to the device + the ctypes job describing it (keeps tensors alive)."""
+_KM_CACHE = {}            # (device index, key material bytes) -> device tensor; small shared-key material only
+_KM_CACHE_MAX = 1024
 
-    def __init__(self, km: KeyMaterial, n_latents: int, n_elems: int, device: torch.device):
+
+def _upload_key_material(packed: np.ndarray, device: torch.device) -> torch.Tensor:
+    """[keys | nonces | msgs] on the device.  Shared key material (a few dozen bytes, the reference's usual case: one
+    --key_hex / --nonce_hex / --message per run) is uploaded ONCE per device and reused by every later call with the same
+    bytes, so a call site that is invoked per latent enqueues nothing but its kernel -- no synchronous pageable copy in
+    front of it, which also keeps programmatic dependent launch working between consecutive calls."""
+    if packed.nbytes > 4096:
+        return torch.from_numpy(packed).to(device, non_blocking=False)
+    ck = (device.index, packed.tobytes())
+    t = _KM_CACHE.get(ck)
+    if t is None:
+        if len(_KM_CACHE) >= _KM_CACHE_MAX:      # kernels on any stream may still be reading an entry: drain before dropping them
+            torch.cuda.synchronize(device)
+            _KM_CACHE.clear()
+        t = torch.from_numpy(packed).to(device, non_blocking=False)
+        _KM_CACHE[ck] = t
+    return t
+
+
+class _DeviceJob:
+    """Key material on the device + the ctypes job describing it (keeps the tensor alive)."""
+
+    def __init__(self, km: KeyMaterial, n_latents: int, n_elems: int, device: torch.device, keys_in_flight: bool = False):
         if km.per_latent and km.rows != n_latents:
             raise ValueError(f"per-latent key material has {km.rows} rows for {n_latents} latents")
         packed = [km.keys.reshape(-1), km.nonces.reshape(-1)]
         if km.msgs is not None:
             packed.append(km.msgs.reshape(-1))
-        # one H2D copy for all three arrays (each segment stays 4-byte aligned: 32 | 16 | msg_bits/8 rows)
-        flat = torch.from_numpy(np.concatenate(packed)).to(device, non_blocking=False)
+        # one buffer for all three arrays (keys and nonces are 32 / 16 bytes per row: the message segment stays 4-byte aligned)
+        flat = _upload_key_material(np.concatenate(packed), device)
         self.flat = flat
         o1 = km.keys.size
         o2 = o1 + km.nonces.size
-        self.job = Job(n_latents, n_elems, km.msg_bits, 1 if km.per_latent else 0,
+        flags = (_lib.JOB_PER_LATENT if km.per_latent else 0) | (_lib.JOB_KEYS_IN_FLIGHT if keys_in_flight else 0)
+        self.job = Job(n_latents, n_elems, km.msg_bits, flags,
                        flat.data_ptr(), flat.data_ptr() + o1, (flat.data_ptr() + o2) if km.msgs is not None else None)
-        ws_bytes = _lib.lib().gswm_workspace_bytes(C.byref(self.job))
-        self.workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device) if ws_bytes else None
-
-    @property
-    def ws_ptr(self):
-        return self.workspace.data_ptr() if self.workspace is not None else None
 
 
 def _device(device) -> torch.device:
@@ -194,9 +213,9 @@ def embed_batch(n_latents: int, latent_shape: Sequence[int], km: KeyMaterial, se
         if n_latents == 0:                       # an empty batch is valid and launches nothing
             return out
         _lib.check(_lib.lib().gswm_embed(C.byref(dj.job), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), first_latent,
-                                         out.data_ptr(), dj.ws_ptr, _stream_ptr(dev)), "gswm_embed")
-        # key material / workspace are freed when dj goes out of scope; the caching allocator keeps the
-        # blocks tied to this stream, so reuse is stream-ordered.
+                                         out.data_ptr(), _stream_ptr(dev)), "gswm_embed")
+        # per-latent key material is freed when dj goes out of scope; the caching allocator keeps the block tied to this
+        # stream, so reuse is stream-ordered.
     return out
 
 
@@ -218,8 +237,59 @@ def embed_batch_injected(u: torch.Tensor, latent_shape: Sequence[int], km: KeyMa
         dj = _DeviceJob(km, n_latents, n, dev)
         out = torch.empty((n_latents, *latent_shape), dtype=out_dtype, device=dev)
         _lib.check(_lib.lib().gswm_embed_injected(C.byref(dj.job), u.data_ptr(), 0 if shared_u else 1, out.data_ptr(),
-                                                  _DTYPE_CODE[out_dtype], dj.ws_ptr, _stream_ptr(dev)),
+                                                  _DTYPE_CODE[out_dtype], _stream_ptr(dev)),
                    "gswm_embed_injected")
+    return out
+
+
+def _seed_args(seeds, n: int, dev: torch.device):
+    """(device tensor or None, seed0) for the MT19937 entry points.  numpy's legacy seeding takes integers in [0, 2^32)
+    (anything else raises ValueError there too)."""
+    if isinstance(seeds, (int, np.integer)):
+        if not 0 <= int(seeds) <= 0xFFFFFFFF:
+            raise ValueError("Seed must be between 0 and 2**32 - 1")
+        return None, int(seeds)
+    arr = np.ascontiguousarray(seeds, dtype=np.int64).reshape(-1)
+    if arr.size != n:
+        raise ValueError(f"need one seed per stream ({n}), got {arr.size}")
+    if arr.size and (arr.min() < 0 or arr.max() > 0xFFFFFFFF):
+        raise ValueError("Seed must be between 0 and 2**32 - 1")
+    return torch.from_numpy(arr.astype(np.uint32).view(np.int32)).to(dev), 0
+
+
+def mt19937_uniform(seeds, n_each: int, n_streams: Optional[int] = None, device="cuda") -> torch.Tensor:
+    """[n_streams, n_each] float64 on the device: row s is ``np.random.RandomState(seed_s).uniform(size=n_each)`` bit for
+    bit (MT19937, init_genrand seeding, 53-bit doubles).  ``seeds``: one int (stream s uses seed + s) or one per stream."""
+    dev = _device(device)
+    if n_streams is None:
+        n_streams = 1 if isinstance(seeds, (int, np.integer)) else len(seeds)
+    with torch.cuda.device(dev):
+        d_seeds, seed0 = _seed_args(seeds, n_streams, dev)
+        out = torch.empty((n_streams, n_each), dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().gswm_mt19937_uniform(d_seeds.data_ptr() if d_seeds is not None else None, seed0, n_streams,
+                                                   n_each, out.data_ptr(), _stream_ptr(dev)), "gswm_mt19937_uniform")
+    return out
+
+
+def embed_batch_mt19937(seeds, n_latents: int, latent_shape: Sequence[int], km: KeyMaterial,
+                        out_dtype: torch.dtype = torch.float32, device="cuda") -> torch.Tensor:
+    """The reference's SEEDED embed for a batch, entirely on the device: latent b draws its uniforms from
+    ``np.random.RandomState(seed_b)`` element by element (nodes.py:52-53,114-117; v1.5.2:27,72-75) -- generated by the
+    MT19937 kernel, nothing uploaded -- and z = norm.ppf((u + y) / 2) is evaluated in float64 (gs_insert.py:64).
+    ``seeds``: one int (latent b uses seed + b) or one per latent."""
+    dev = _device(device)
+    n = _n_elems(latent_shape)
+    if km.msg_bits % 32:
+        raise ValueError("embedding needs a message length that is a multiple of 32 bits")
+    with torch.cuda.device(dev):
+        d_seeds, seed0 = _seed_args(seeds, n_latents, dev)
+        dj = _DeviceJob(km, n_latents, n, dev)
+        out = torch.empty((n_latents, *latent_shape), dtype=out_dtype, device=dev)
+        if n_latents == 0:
+            return out
+        _lib.check(_lib.lib().gswm_embed_mt19937(C.byref(dj.job), d_seeds.data_ptr() if d_seeds is not None else None, seed0,
+                                                 out.data_ptr(), _DTYPE_CODE[out_dtype], _stream_ptr(dev)),
+                   "gswm_embed_mt19937")
     return out
 
 
@@ -228,11 +298,16 @@ class ExtractResult:
     messages: torch.Tensor            # uint8 [B, msg_bits/8], MSB-first packed decoded bits
     counts: Optional[torch.Tensor]    # uint16 [B, msg_bits] count_1 per position
     matched: Optional[torch.Tensor]   # int32 [B] bits equal to the reference message
-    counters: torch.Tensor            # int64 [4]: matched_bits, total_bits, exact_msgs, total_msgs
+    counters: torch.Tensor            # int64 [6]: matched_bits, total_bits, exact_msgs, total_msgs, nan_latents, range_latents
+    flags: Optional[torch.Tensor] = None   # uint8 [B]: FLAG_NAN / FLAG_RANGE -- inputs the reference raises on (extract.py:83,86)
+    msg_bits: int = 0
+    reduced: Optional[torch.Tensor] = None # int64 [6]: the counters summed over the ranks of a Comm (extract_batch(comm=...))
 
     def bit_strings(self):
         """Decoded messages as the '0'/'1' strings extract.recover_exactracted_message returns."""
         bits = np.unpackbits(self.messages.cpu().numpy(), axis=1)
+        if self.msg_bits:
+            bits = bits[:, :self.msg_bits]          # a length that is not a whole number of bytes ends inside the last byte
         return ["".join("1" if b else "0" for b in row) for row in bits]
 
     def bit_accuracy(self) -> float:
@@ -241,8 +316,11 @@ class ExtractResult:
 
 
 def extract_batch(z: torch.Tensor, km: KeyMaterial, want_counts: bool = False,
-                  counters: Optional[torch.Tensor] = None) -> ExtractResult:
-    """Decode a batch of inverted latents ``z`` [B, ...] (fp32 / fp16 / bf16 / fp64, CUDA)."""
+                  counters: Optional[torch.Tensor] = None, comm: Optional["Comm"] = None) -> ExtractResult:
+    """Decode a batch of inverted latents ``z`` [B, ...] (fp32 / fp16 / bf16 / fp64, CUDA).  ``flags`` marks the
+    latents the reference would refuse (a NaN, or an element >= 8.2924); they are decoded all the same with
+    bit = (z >= threshold).  With ``comm`` the cross-GPU sum of the accumulated counters is fused into the same
+    kernel (gswm_extract_allreduce) and returned as ``result.reduced``."""
     if not z.is_cuda:
         raise ValueError("z must be a CUDA tensor (there is no CPU path)")
     if z.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
@@ -253,20 +331,28 @@ def extract_batch(z: torch.Tensor, km: KeyMaterial, want_counts: bool = False,
     n = _n_elems(z.shape[1:])
     if n % km.msg_bits:
         raise ValueError("message length must divide the latent size")
+    row = (km.msg_bits + 7) // 8
     with torch.cuda.device(dev):
         dj = _DeviceJob(km, b, n, dev)
-        msgs = torch.empty((b, km.msg_bits // 8), dtype=torch.uint8, device=dev)
+        msgs = torch.empty((b, row), dtype=torch.uint8, device=dev)
         cnt = torch.empty((b, km.msg_bits), dtype=torch.uint16, device=dev) if want_counts else None
         matched = torch.empty((b,), dtype=torch.int32, device=dev) if km.msgs is not None else None
+        flags = torch.empty((b,), dtype=torch.uint8, device=dev)
         if counters is None:
             counters = torch.zeros((_lib.N_COUNTERS,), dtype=torch.int64, device=dev)
-        if b == 0:                               # an empty batch is valid and launches nothing
-            return ExtractResult(msgs, cnt, matched, counters)
-        _lib.check(_lib.lib().gswm_extract(C.byref(dj.job), z.data_ptr(), _DTYPE_CODE[z.dtype], msgs.data_ptr(),
-                                           cnt.data_ptr() if cnt is not None else None,
-                                           matched.data_ptr() if matched is not None else None,
-                                           counters.data_ptr(), dj.ws_ptr, _stream_ptr(dev)), "gswm_extract")
-    return ExtractResult(msgs, cnt, matched, counters)
+        res = ExtractResult(msgs, cnt, matched, counters, flags, km.msg_bits)
+        if b == 0 and comm is None:              # an empty batch is valid and launches nothing
+            return res
+        args = (C.byref(dj.job), z.data_ptr(), _DTYPE_CODE[z.dtype], msgs.data_ptr(),
+                cnt.data_ptr() if cnt is not None else None, matched.data_ptr() if matched is not None else None,
+                flags.data_ptr(), counters.data_ptr())
+        if comm is None:
+            _lib.check(_lib.lib().gswm_extract(*args, _stream_ptr(dev)), "gswm_extract")
+        else:
+            res.reduced = torch.empty((_lib.N_COUNTERS,), dtype=torch.int64, device=dev)
+            _lib.check(_lib.lib().gswm_extract_allreduce(*args, comm.handle, res.reduced.data_ptr(), _stream_ptr(dev)),
+                       "gswm_extract_allreduce")
+    return res
 
 
 _side_streams = {}
@@ -297,7 +383,7 @@ def embed_extract_batch(n_latents: int, latent_shape: Sequence[int], km_embed: K
     join = torch.cuda.Event()
     join.record(side)
     cur.wait_event(join)
-    for t in (res.messages, res.counts, res.matched, res.counters):
+    for t in (res.messages, res.counts, res.matched, res.counters, res.flags):
         if t is not None:
             t.record_stream(cur)
     return z_out, res
@@ -331,7 +417,7 @@ class HostPipe:
             raise ValueError("per-latent key material row count != n_latents")
         keep = (np.ascontiguousarray(km.keys), np.ascontiguousarray(km.nonces),
                 None if km.msgs is None else np.ascontiguousarray(km.msgs))
-        job = Job(n_latents, n_elems, km.msg_bits, 1 if km.per_latent else 0, keep[0].ctypes.data, keep[1].ctypes.data,
+        job = Job(n_latents, n_elems, km.msg_bits, _lib.JOB_PER_LATENT if km.per_latent else 0, keep[0].ctypes.data, keep[1].ctypes.data,
                   keep[2].ctypes.data if keep[2] is not None else None)
         return job, keep
 
@@ -368,8 +454,8 @@ class HostPipe:
         return out
 
     def extract(self, z: Union[np.ndarray, torch.Tensor], km: KeyMaterial, want_counts: bool = False):
-        """Decode host latents [B, ...]; returns (messages u8 [B, L/8], counts u16 or None, matched i32 or None,
-        counters i64[4]) as numpy arrays."""
+        """Decode host latents [B, ...]; returns (messages u8 [B, ceil(L/8)], counts u16 or None, matched i32 or None,
+        counters i64[6], flags u8 [B]) as numpy arrays."""
         t = torch.from_numpy(z) if isinstance(z, np.ndarray) else z
         if t.is_cuda or t.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
             raise ValueError("z must be a host fp32 / fp16 / bf16 / fp64 array")
@@ -377,15 +463,73 @@ class HostPipe:
         b = t.shape[0]
         n = _n_elems(t.shape[1:])
         job, keep = self._host_job(km, b, n)
-        msgs = np.empty((b, km.msg_bits // 8), dtype=np.uint8)
+        msgs = np.empty((b, (km.msg_bits + 7) // 8), dtype=np.uint8)
         cnt = np.empty((b, km.msg_bits), dtype=np.uint16) if want_counts else None
         matched = np.empty((b,), dtype=np.int32) if km.msgs is not None else None
+        flags = np.zeros((b,), dtype=np.uint8)
         counters = np.zeros((_lib.N_COUNTERS,), dtype=np.int64)
         if b == 0:
-            return msgs, cnt, matched, counters
+            return msgs, cnt, matched, counters, flags
         _lib.check(_lib.lib().gswm_pipe_extract(self._p, C.byref(job), t.data_ptr(), _DTYPE_CODE[t.dtype], msgs.ctypes.data,
                                                 cnt.ctypes.data if cnt is not None else None,
                                                 matched.ctypes.data if matched is not None else None,
-                                                counters.ctypes.data), "gswm_pipe_extract")
+                                                flags.ctypes.data, counters.ctypes.data), "gswm_pipe_extract")
         del keep
-        return msgs, cnt, matched, counters
+        return msgs, cnt, matched, counters, flags
+
+
+# ----------------------------------------------------------------------------- multi-GPU
+class Comm:
+    """gswm_comm: per-rank mailboxes mapped over NVLink (include/gswm.h, "Multi-GPU").  One instance per rank; the
+    CUDA IPC handles are exchanged through ``torch.distributed`` (any initialised backend), which is used for that
+    rendezvous only -- the all-reduce itself is a gswm kernel storing into the peers' memory."""
+
+    def __init__(self, device=None, group=None):
+        import torch.distributed as dist
+
+        dev = _device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        self.device = dev
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self._h = C.c_void_p()
+        handle = (C.c_uint8 * _lib.COMM_HANDLE_BYTES)()
+        _lib.check(_lib.lib().gswm_comm_create(C.byref(self._h), dev.index, self.rank, self.world, handle), "gswm_comm_create")
+        if self.world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8)
+            backend = dist.get_backend(group)
+            if backend == "nccl":
+                mine = mine.to(dev)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=group)
+            blob = torch.cat([g.cpu() for g in gathered]).numpy().tobytes()
+            buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+            _lib.check(_lib.lib().gswm_comm_connect(self._h, buf), "gswm_comm_connect")
+            dist.barrier(group=group)            # every rank has mapped every mailbox before anyone publishes
+
+    @property
+    def handle(self):
+        return self._h
+
+    def allreduce_counters(self, counters: torch.Tensor) -> torch.Tensor:
+        """Sum ``counters`` (int64, <= 8 values, on this rank's device) over all ranks, in place, on the current stream."""
+        if counters.dtype != torch.int64 or not counters.is_cuda or not counters.is_contiguous():
+            raise ValueError("counters must be a contiguous int64 CUDA tensor")
+        _lib.check(_lib.lib().gswm_comm_allreduce_counters(self._h, counters.data_ptr(), counters.numel(),
+                                                           _stream_ptr(counters.device)), "gswm_comm_allreduce_counters")
+        return counters
+
+    def status(self) -> int:
+        return int(_lib.lib().gswm_comm_status(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lib().gswm_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -35,21 +35,36 @@ def gs_watermark_init_noise(key_hex, nonce_hex, device, message, use_seed, rando
     placement exactly as in the reference (it builds on ``device`` and returns ``.cpu()``)."""
     n, bits, k = _frame(message, width, height, message_length)
     key, nonce = codec.resolve_key_nonce(key_hex, nonce_hex)                        # nodes.py:90-99
-    u = common.draw_uniforms(n, int(use_seed) == 1, randomSeed)                     # nodes.py:52-53,114-117
-    z = common.embed_injected(u, (4, height // 8, width // 8), key, nonce, k, bits, 1, torch.float32)
+    shape = (4, height // 8, width // 8)
+    if int(use_seed) == 1:                                                          # nodes.py:52-53,117: RandomState(randomSeed)
+        z = common.embed_seeded(randomSeed, shape, key, nonce, k, bits, torch.float32)
+    else:                                                                           # nodes.py:115: numpy's global generator
+        z = common.embed_injected(common.draw_uniforms(n, False, None), shape, key, nonce, k, bits, 1, torch.float32)
     _log(key, nonce, k, randomSeed, height, width, message_length)
     return z[0].cpu()
 
 
-def gs_watermark_init_noise_batch(key_hex, nonce_hex, message, batch_size, width, height, message_length=-1):
-    """batch_size independent unseeded latents (nodes.py:237) as one launch: (B, 4, h, w) fp32 CPU tensor.
+def gs_watermark_init_noise_batch(key_hex, nonce_hex, message, batch_size, width, height, message_length=-1,
+                                  randomSeed=None):
+    """batch_size independent unseeded latents -- the list comprehension of nodes.py:236-237 -- as one launch:
+    (B, 4, h, w) fp32 CPU tensor.  What the reference does batch_size times is done batch_size times here too:
+    an empty ``message`` draws a fresh ``os.urandom`` message per latent (nodes.py:76) and an empty ``key_hex`` a fresh
+    key and nonce per latent (nodes.py:97-98), in the reference's call order (message, key, nonce); each latent gets
+    its own ``info_data.txt`` record, with the widget's ``randomSeed`` passed through as nodes.py:131,134 log it.
     Uniforms come from numpy's global generator in the order the reference's sequential calls would draw them."""
-    n, bits, k = _frame(message, width, height, message_length)
-    key, nonce = codec.resolve_key_nonce(key_hex, nonce_hex)
+    n = 4 * (width // 8) * (height // 8)
+    rows = batch_size if (not message or not key_hex) else 1      # one row serves the whole batch when nothing is random
+    ks, keys, nonces = [], [], []
+    for _ in range(rows):
+        _, bits, k = _frame(message, width, height, message_length)
+        key, nonce = codec.resolve_key_nonce(key_hex, nonce_hex)
+        ks.append(k), keys.append(key), nonces.append(nonce)
     u = common.draw_uniforms(n, False, None, copies=batch_size).reshape(batch_size, n)
-    z = common.embed_injected(u, (4, height // 8, width // 8), key, nonce, k, bits, batch_size, torch.float32)
-    for _ in range(batch_size):
-        _log(key, nonce, k, None, height, width, message_length)
+    z = common.embed_injected(u, (4, height // 8, width // 8), b"".join(keys), b"".join(nonces), b"".join(ks), bits,
+                              batch_size, torch.float32)
+    for i in range(batch_size):
+        r = i if rows > 1 else 0
+        _log(keys[r], nonces[r], ks[r], randomSeed, height, width, message_length)
     return z.cpu()
 
 
@@ -161,7 +176,8 @@ class GSLatent:
             batch = one.float().unsqueeze(0).repeat(batch_size, 1, 1, 1)
         else:
             # batch_size independent latents (nodes.py:237): one launch instead of batch_size calls
-            batch = gs_watermark_init_noise_batch(key, nonce, message, batch_size, width, height, message_length).float()
+            batch = gs_watermark_init_noise_batch(key, nonce, message, batch_size, width, height, message_length,
+                                                  randomSeed=seed).float()
         return ({"samples": batch}, batch[0])
 
 

@@ -9,11 +9,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import codec
-
-# int(norm.cdf(z) * 2) is 1 from this float64 value upwards and 2 (reference crashes) from the second
-_CDF_HALF = -6.957291061679417e-17
-_CDF_ONE = 8.292361075813597
+from . import _lib, codec
 
 
 def _as_tensor(reversed_latents) -> torch.Tensor:
@@ -22,33 +18,51 @@ def _as_tensor(reversed_latents) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(reversed_latents))
 
 
+def _rejection(flag: int):
+    """The exception the reference ends in for a latent the kernel flagged (extract.py:83 / :86)."""
+    if flag & _lib.FLAG_NAN:
+        return ValueError("cannot convert float NaN to integer")
+    if flag & _lib.FLAG_RANGE:
+        return ValueError("invalid literal for int() with base 2: int(norm.cdf(z) * 2) == 2 for an element >= 8.2924")
+    return None
+
+
+def _decode(reversed_latents, args, batched: bool):
+    """Shared front end: dtype / length checks in the reference's order, one extract launch, results + per-latent flags."""
+    if int(args.l) != 1:
+        # extract.py:84-86 emits digits >= 2 into a base-2 parse for l > 1: non-functional upstream
+        raise ValueError("invalid literal for int() with base 2 (window size l must be 1)")
+    z = _as_tensor(reversed_latents)
+    z = z.reshape(z.shape[0], -1) if batched else z.reshape(1, -1)
+    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
+        z = z.to(torch.float32)                     # integer tensors etc.; float64 is decoded as float64 on the device
+    msg_bits = int(args.message_length)
+    if msg_bits <= 0 or z.shape[1] % msg_bits:
+        # extract.py:94,98: the short last segment is indexed past its end
+        raise IndexError("string index out of range")
+    if (z.shape[1] * z.element_size()) % 16:
+        z = z.to(torch.float32)                     # odd-sized 16-bit rows: the kernel fetches rows in 16-byte pieces (exact upcast)
+    km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)
+    dev = z.device if z.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    res = codec.extract_batch(z.to(dev), km)
+    return res, res.flags.cpu().numpy()
+
+
 def recover_exactracted_message(reversed_latents, args) -> str:
     """extract.py:72-101.  ``reversed_latents``: the inverted latent, any shape that flattens (C
     order, as np.nditer walks it) to the embedded element order -- normally a (1, 4, h, w) fp16 CPU
     tensor (extract.py:48,70).  ``args`` carries ``key``, ``nonce`` (bytes), ``l`` and
-    ``message_length``.  Returns the '0'/'1' string of length message_length.
+    ``message_length`` (any integer that divides the latent size, as in the reference).  Returns the '0'/'1' string
+    of length message_length.
 
     Raises ValueError where the reference does: NaN input (int(nan)) and any z with
     norm.cdf(z) * 2 rounding to 2 (z >= 8.2924, +inf), whose digit '2' breaks int(..., 2) at
-    extract.py:86.
+    extract.py:86 -- both found by the extract kernel in the same pass (GSWM_FLAG_*), not by extra scans of the tensor.
     """
-    if int(args.l) != 1:
-        # extract.py:84-86 emits digits >= 2 into a base-2 parse for l > 1: non-functional upstream
-        raise ValueError("invalid literal for int() with base 2 (window size l must be 1)")
-    z = _as_tensor(reversed_latents).reshape(1, -1)
-    if torch.isnan(z).any():
-        raise ValueError("cannot convert float NaN to integer")
-    if (z >= _CDF_ONE).any():
-        raise ValueError("invalid literal for int() with base 2: cdf(z) * 2 == 2")
-    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
-        z = z.to(torch.float32)                     # integer tensors etc.; float64 is decoded as float64 on the device
-    msg_bits = int(args.message_length)
-    km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)
-    if z.numel() % msg_bits:
-        # extract.py:94,98: the short last segment is indexed past its end
-        raise IndexError("string index out of range")
-    dev = z.device if z.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    res = codec.extract_batch(z.to(dev), km)
+    res, flags = _decode(reversed_latents, args, batched=False)
+    err = _rejection(int(flags[0]))
+    if err is not None:
+        raise err
     return res.bit_strings()[0]
 
 
@@ -76,23 +90,30 @@ def write_batch_info(result_file, args):
 def evaluate_latents(names, reversed_latents, args, result_file=None):
     """Batched form of the per-image loop in extract.process_single_directory (extract.py:134-163): decode every
     inverted latent of ``reversed_latents`` [B, ...] in one launch and report like the reference does --
-    ``<name>, Bit Accuracy, <acc>`` per image, then ``Average Bit Accuracy, <mean>``.  Returns
-    (extracted bit strings, accuracies, average)."""
-    z = _as_tensor(reversed_latents)
-    z = z.reshape(z.shape[0], -1)
-    if z.dtype not in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
-        z = z.to(torch.float32)
-    msg_bits = int(args.message_length)
-    km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)
-    dev = z.device if z.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    res = codec.extract_batch(z.to(dev), km)
+    ``<name>, Bit Accuracy, <acc>`` per image, then ``Average Bit Accuracy, <mean>``.  An image the reference's
+    ``recover_exactracted_message`` would raise on (NaN / z >= 8.2924) gets the reference's
+    ``Error processing <name>: <exception>`` line instead, is printed, and is left out of the average, exactly like the
+    per-image ``try / except`` at extract.py:148-155.  Returns (extracted bit strings -- None for a rejected image --,
+    accuracies -- None likewise --, average over the accepted ones)."""
+    res, flags = _decode(reversed_latents, args, batched=True)
     strings = res.bit_strings()
-    accs = [calculate_bit_accuracy(args.original_message_hex, s)[1] for s in strings]
-    avg = sum(accs) / len(accs) if accs else 0.0
-    if result_file is not None:
-        for name, acc in zip(names, accs):
+    accs = []
+    for i, (name, s) in enumerate(zip(names, strings)):
+        err = _rejection(int(flags[i]))
+        if err is not None:
+            strings[i] = None
+            accs.append(None)
+            print(f"Error processing {name}: {err}\n")
+            if result_file is not None:
+                result_file.write(f"Error processing {name}: {err}\n")
+            continue
+        acc = calculate_bit_accuracy(args.original_message_hex, s)[1]
+        accs.append(acc)
+        if result_file is not None:
             result_file.write(f"{name}, Bit Accuracy, {acc}\n")
-        if accs:
-            result_file.write(f"Average Bit Accuracy, {avg}\n\n")
-            result_file.write("=" * 40 + "Batch End" + "=" * 40 + "\n")
+    good = [a for a in accs if a is not None]
+    avg = sum(good) / len(good) if good else 0.0
+    if result_file is not None and good:
+        result_file.write(f"Average Bit Accuracy, {avg}\n\n")
+        result_file.write("=" * 40 + "Batch End" + "=" * 40 + "\n")
     return strings, accs, avg

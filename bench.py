@@ -327,14 +327,12 @@ def run_gpu_arm(args):
     z = torch.empty((B, *shape), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
-    gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
+    gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
     g = torch.Generator(dev).manual_seed(99 + rank)
     z_noisy = z + SIGMA * torch.randn(z.shape, device=dev, generator=g)
     msgs = torch.empty((B, L // 8), dtype=torch.uint8, device=dev)
     matched = torch.empty((B,), dtype=torch.int32, device=dev)
-    counters = torch.zeros((4,), dtype=torch.int64, device=dev)
-    ws2 = torch.empty_like(dj.workspace) if dj.workspace is not None else None
-    ws2p = ws2.data_ptr() if ws2 is not None else None
+    counters = torch.zeros((gswm._lib.N_COUNTERS,), dtype=torch.int64, device=dev)
 
     # The two halves of a step are independent (embed writes z, extract reads z_noisy), one is bound by the FMA pipes
     # and the other by HBM, so they are launched on two streams and share the SMs: the step then runs at the pair's
@@ -343,9 +341,9 @@ def run_gpu_arm(args):
     xp = xstream.cuda_stream
 
     def step(serial=False):
-        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
+        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
         gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
-                                         counters.data_ptr(), ws2p, sp if serial else xp), "gswm_extract")
+                                         None, counters.data_ptr(), sp if serial else xp), "gswm_extract")
 
     def timed(n_steps, serial=False, reduce=True):
         """Device time of n_steps steps: fork the extract stream off the launch stream, join it back before the end event.
@@ -410,11 +408,11 @@ def run_gpu_arm(args):
         return e0.elapsed_time(e1) / inst_steps
 
     def launch_embed():
-        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), dj.ws_ptr, sp), "gswm_embed")
+        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
 
     def launch_extract():
         gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
-                                         counters.data_ptr(), ws2p, sp), "gswm_extract")
+                                         None, counters.data_ptr(), sp), "gswm_extract")
 
     embed_bursts = sorted(burst(launch_embed) for _ in range(3))
     extract_bursts = sorted(burst(launch_extract) for _ in range(3))
@@ -455,7 +453,7 @@ def run_gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        _, _, _, h_cnt = e2e_step()
+        _, _, _, h_cnt, _ = e2e_step()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:

@@ -240,7 +240,7 @@ GSWM_PHILOX_ROUNDS = 7           # csrc/gswm_math.cuh default (Philox4x32-7, the
 
 def gswm_uniform_ints(seed: int, offset: int, latent_index: int, n_elems: int,
                       rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
-    """The 23-bit integer m of every element of one latent ("gswm uniforms v2", csrc/gswm_math.cuh).
+    """The 23-bit integer m of every element of one latent ("gswm uniforms v3", csrc/gswm_math.cuh).
 
     The latent is cut into tiles of 16384 elements; a tile into 4 super-iterations of 256 lanes; lane `tid`
     of super-iteration `s` owns the four float4 (16 elements) at within-tile float4 indices
@@ -273,14 +273,43 @@ def gswm_uniform_ints(seed: int, offset: int, latent_index: int, n_elems: int,
     return m.reshape(-1)[:n_elems]
 
 
+GSWM_TOP_CELL = (1 << 23) - 1   # the outermost grid cell, subdivided by "gswm uniforms v3"
+
+
+def gswm_top_cell_words(seed: int, offset: int, latent_index: int, n_elems: int, elems: np.ndarray,
+                        rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
+    """The 32 refinement bits of elements `elems` (flat indices into one latent) should they fall in the outermost cell:
+    word j of Philox4x32(ctr = (G_lo, G_hi, offset_lo, (offset_hi << 2) + 3), key = (seed_lo, seed_hi + k)), where the
+    element is number j of float4 k of the super-iteration with counter G (see gswm_uniform_ints)."""
+    elems = np.asarray(elems, dtype=np.int64).reshape(-1)
+    tiles = (n_elems + GSWM_TILE - 1) // GSWM_TILE
+    tile, within = elems // GSWM_TILE, elems % GSWM_TILE
+    f4, j = within // 4, within % 4
+    tid, sk = f4 % 256, f4 // 256
+    s_, k = sk // 4, sk % 4
+    out = np.empty(elems.size, dtype=np.uint32)
+    for i in range(elems.size):
+        g = ((latent_index * tiles + int(tile[i])) * 4 + int(s_[i])) * 256 + int(tid[i])
+        ctr = np.array([[g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF, offset & 0xFFFFFFFF, (((offset >> 32) << 2) + 3) & 0xFFFFFFFF]],
+                       dtype=np.uint32)
+        key = (seed & 0xFFFFFFFF, ((seed >> 32) + int(k[i])) & 0xFFFFFFFF)
+        out[i] = philox4x32(ctr, key, rounds)[0, int(j[i])]
+    return out
+
+
 def gswm_uniforms(seed: int, offset: int, latent_index: int, y: np.ndarray,
                   rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
-    """float64 u in (0,1) for every element of one latent, given its bucket bits y:
-    v = (m + 1/2) 2^-23;  u = v where y == 1, u = 1 - v where y == 0 (both exact in float64)."""
+    """float64 u in (0,1) for every element of one latent, given its bucket bits y ("gswm uniforms v3"):
+    v = (m + 1/2) 2^-23;  u = v where y == 1, u = 1 - v where y == 0 (both exact in float64).  An element in the
+    outermost cell m = 2^23 - 1 is refined by 28 more bits: 1 - v = (m2 + 1/2) 2^-51, m2 = refinement word >> 4."""
     y = np.asarray(y).reshape(-1)
     m = gswm_uniform_ints(seed, offset, latent_index, y.size, rounds)
-    v = (m.astype(np.float64) + 0.5) * 2.0 ** -23
-    return np.where(y == 1, v, 1.0 - v)
+    one_minus_v = (np.float64(1 << 23) - m.astype(np.float64) - 0.5) * 2.0 ** -23
+    top = np.flatnonzero(m == GSWM_TOP_CELL)
+    if top.size:
+        w = gswm_top_cell_words(seed, offset, latent_index, y.size, top, rounds)
+        one_minus_v[top] = ((w >> np.uint32(4)).astype(np.float64) + 0.5) * 2.0 ** -51
+    return np.where(y == 1, 1.0 - one_minus_v, one_minus_v)
 
 
 def embed_gswm(message, key: bytes, nonce16: bytes, seed: int, offset: int, latent_index: int, n_elems: int,
@@ -318,6 +347,16 @@ def vote_counts(z: np.ndarray, key: bytes, nonce16: bytes, l_bits: int, keystrea
     s_d = m ^ keystream(key, nonce16, m.size)
     all_bits = np.unpackbits(s_d)
     return all_bits.reshape(-1, l_bits).sum(axis=0).astype(np.uint32)
+
+
+def vote_counts_batch(z: np.ndarray, key: bytes, nonce16: bytes, l_bits: int, keystream=chacha20_keystream) -> np.ndarray:
+    """vote_counts for a batch [B, N] that shares one key / nonce: the keystream is produced once (extract.py:77-78 builds
+    one cipher per call; the bytes are the same), everything else is the per-latent arithmetic of extract.py:82-98."""
+    z = np.asarray(z)
+    b, n = z.shape[0], int(np.prod(z.shape[1:]))
+    bits = np.stack([quantise(z[i].reshape(-1)) for i in range(b)])
+    ks = np.unpackbits(np.frombuffer(bytes(keystream(key, nonce16, (n + 7) // 8)), dtype=np.uint8))[:n]
+    return (bits ^ ks[None, :]).reshape(b, n // l_bits, l_bits).sum(axis=1).astype(np.uint32)
 
 
 def recover_message_bits(z: np.ndarray, key: bytes, nonce16: bytes, l_bits: int,

@@ -106,6 +106,22 @@ class _Replay:
         return v
 
 
+class _FakeUrandom:
+    """Deterministic stand-in for os.urandom: call i returns the first n bytes of sha256-counter-mode stream i
+    (tests/test_gpu_parity.py installs the same patch around the drop-in)."""
+
+    def __init__(self):
+        self.calls = 0
+
+    def __call__(self, n):
+        out, block = b"", 0
+        while len(out) < n:
+            out += hashlib.sha256(b"gswm-golden-urandom %d %d" % (self.calls, block)).digest()
+            block += 1
+        self.calls += 1
+        return out[:n]
+
+
 def sha(a) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -223,6 +239,35 @@ def main():
         lat, first = nodes.GSLatent().create_gs_latents(KEY_HEX, NONCE_HEX, "lthero", 3, 1, 42, 512, 512, 256)
         out["gslatent_seeded"] = {"shape": list(lat["samples"].shape), "sha256": sha(lat["samples"].numpy()),
                                   "first_sha256": sha(first.numpy())}
+        # GSLatent node, UNSEEDED: batch_size independent calls (nodes.py:236-237), uniforms from numpy's global
+        # generator (seeded here so the run is reproducible); the widget's seed is still passed through and logged.
+        np.random.seed(2024)
+        lat, first = nodes.GSLatent().create_gs_latents(KEY_HEX, NONCE_HEX, "lthero", 3, 0, 77, 512, 512, 256)
+        s = lat["samples"].numpy()
+        arrays["gslatent_unseeded_heads"] = s.reshape(3, -1)[:, :128].copy()
+        with open("info_data.txt") as f:
+            tail = f.read().splitlines()[-30:]
+        out["gslatent_unseeded"] = {"np_seed": 2024, "batch_size": 3, "widget_seed": 77, "shape": list(s.shape),
+                                    "sha256": sha(s), "first_sha256": sha(first.numpy()),
+                                    "sha256_signs_each": [sha(packed_signs(s[i])) for i in range(3)],
+                                    "info_data_tail": tail}
+        # ... with an EMPTY message and an EMPTY key: every one of the batch_size calls draws its own os.urandom message,
+        # key and nonce (nodes.py:76,97-98).  os.urandom is replaced by a counter-mode sha256 stream so that the run can be
+        # repeated by the drop-in's test (same patch, same call order: message, key, nonce per latent).
+        real_urandom = os.urandom
+        os.urandom = _FakeUrandom()
+        try:
+            np.random.seed(2025)
+            lat, first = nodes.GSLatent().create_gs_latents("", "", "", 2, 0, 5, 256, 256, -1)
+        finally:
+            os.urandom = real_urandom
+        s = lat["samples"].numpy()
+        arrays["gslatent_unseeded_random_heads"] = s.reshape(2, -1)[:, :128].copy()
+        with open("info_data.txt") as f:
+            tail = f.read().splitlines()[-20:]
+        out["gslatent_unseeded_random"] = {"np_seed": 2025, "batch_size": 2, "widget_seed": 5, "shape": list(s.shape),
+                                           "sha256": sha(s), "sha256_signs_each": [sha(packed_signs(s[i])) for i in range(2)],
+                                           "info_data_tail": tail}
 
         # ---------------- webui <=1.5.2 init_gs_Z_s_T (use_repeat + seeded) -------------
         we = []

@@ -176,6 +176,22 @@ def test_embed_injected_golden(gswm, cuda_device, golden, golden_arrays):
     assert sha(packed) == c["sha256_signs"]
 
 
+def test_config2_injected_parity_subset_64_latents(gswm, cuda_device):
+    """the first 64 samples re-run in injected-uniform mode with u = RandomState(1234 + b).uniform
+    (float64) and compared with the oracle element by element: bucket membership exact, values <= 1e-6 relative as fp32
+    and <= 1e-9 as float64."""
+    b, n = 64, 16384
+    u = np.stack([np.random.RandomState(1234 + i).uniform(size=n) for i in range(b)])
+    km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message("lthero", 32), 256)
+    du = torch.from_numpy(u).to(cuda_device)
+    z32 = gswm.embed_batch_injected(du, (4, 64, 64), km, b, torch.float32).cpu().numpy().reshape(b, n)
+    z64 = gswm.embed_batch_injected(du, (4, 64, 64), km, b, torch.float64).cpu().numpy().reshape(b, n)
+    for i in range(b):
+        ref = O.embed("lthero", KEY, NONCE, u[i], 256)
+        assert np.array_equal(z32[i] >= 0, ref >= 0) and np.array_equal(z64[i] >= 0, ref >= 0), i
+        assert rel_err(z32[i], ref.astype(np.float32)).max() <= REL_TOL and rel_err(z64[i], ref).max() <= 1e-9, i
+
+
 def test_embed_injected_edges_and_shared_u(gswm, cuda_device):
     n = 512
     u = np.random.RandomState(5).uniform(size=n)
@@ -237,7 +253,7 @@ def test_extract_counts_vs_oracle(gswm, cuda_device, dtype, shape, L):
         assert int(res.matched[i]) == m
         matched_total += m
     c = res.counters.cpu().numpy()
-    assert list(c) == [matched_total, b * L, int(sum(int(x) == L for x in res.matched.cpu())), b]
+    assert list(c) == [matched_total, b * L, int(sum(int(x) == L for x in res.matched.cpu())), b, 0, 0]
 
 
 def test_extract_per_latent_keys(gswm, cuda_device):
@@ -328,7 +344,7 @@ def test_round_trip_baseline_sizes(gswm, cuda_device):
     km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
     z = gswm.embed_batch(4096, (4, 64, 64), km, 0x5EED, 0, 0, cuda_device)
     res = gswm.extract_batch(z, km)
-    assert list(res.counters.cpu().numpy()) == [4096 * 256, 4096 * 256, 4096, 4096]
+    assert list(res.counters.cpu().numpy()) == [4096 * 256, 4096 * 256, 4096, 4096, 0, 0]
     # moments of the watermarked noise: it must still look like N(0, 1)
     assert abs(float(z.mean())) < 2e-3 and abs(float(z.std()) - 1.0) < 2e-3
     # sigma = 0.325 regime: ~90 % of signs agree, every message still decodes
@@ -337,9 +353,9 @@ def test_round_trip_baseline_sizes(gswm, cuda_device):
     assert 0.89 < agree < 0.91
     res = gswm.extract_batch(noisy, km, want_counts=True)
     assert res.bit_accuracy() == 1.0
-    sub = noisy[:16].cpu().numpy()
-    for i in range(16):
-        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(sub[i], KEY, NONCE, 256))
+    # per-position counts [4096][256] of the WHOLE batch bit-exact against the oracle
+    want = O.vote_counts_batch(noisy.cpu().numpy().reshape(4096, -1), KEY, NONCE, 256)
+    assert np.array_equal(res.counts.cpu().numpy().astype(np.uint32), want)
     # sigma = 4.3 regime: ~90 % of the DECODED bits survive; counts / messages / matched bits of a
     # subset bit-exact against the oracle, and the batch counters equal the sum of the per-latent figures
     heavy = (z + 4.3 * torch.randn(z.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(7))).clamp(max=8.0)
@@ -348,17 +364,19 @@ def test_round_trip_baseline_sizes(gswm, cuda_device):
     c = res.counters.cpu().numpy()
     assert int(c[0]) == int(res.matched.sum()) and int(c[1]) == 4096 * 256 and int(c[3]) == 4096
     assert int(c[2]) == int((res.matched == 256).sum())
-    sub = heavy[:16].cpu().numpy()
     ref_bits = np.unpackbits(np.frombuffer(msg, np.uint8))
-    for i in range(16):
-        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(sub[i], KEY, NONCE, 256))
-        bits = O.recover_message_bits(sub[i], KEY, NONCE, 256)
-        assert O.bits_to_bytes(bits) == res.messages[i].cpu().numpy().tobytes()
-        assert int(res.matched[i]) == int((bits == ref_bits).sum())
+    want = O.vote_counts_batch(heavy.cpu().numpy().reshape(4096, -1), KEY, NONCE, 256)      # all 4096 latents
+    assert np.array_equal(res.counts.cpu().numpy().astype(np.uint32), want)
+    want_bits = (want > 64 / 2).astype(np.uint8)                                            # extract.py:99, R = 64
+    assert np.array_equal(np.unpackbits(res.messages.cpu().numpy(), axis=1), want_bits)
+    assert np.array_equal(res.matched.cpu().numpy(), (want_bits == ref_bits[None, :]).sum(axis=1))
+    sub = heavy[:4].cpu().numpy()
+    for i in range(4):                                                                      # and the per-latent oracle form agrees
+        assert np.array_equal(want[i], O.vote_counts(sub[i], KEY, NONCE, 256))
     del z, noisy, heavy
     zx = gswm.embed_batch(512, (4, 128, 128), km, 1, 0, 0, cuda_device)
     rx = gswm.extract_batch(zx, km)
-    assert list(rx.counters.cpu().numpy()) == [512 * 256, 512 * 256, 512, 512]
+    assert list(rx.counters.cpu().numpy()) == [512 * 256, 512 * 256, 512, 512, 0, 0]
 
 
 def test_watermarked_noise_is_standard_normal(gswm, cuda_device):
@@ -446,7 +464,7 @@ def test_back_to_back_jobs_with_changing_keys(gswm, cuda_device):
     for shape, L, b, per, key, nonce, msg, z0, res in jobs:
         want = msg if per else msg * b
         assert res.messages.cpu().numpy().tobytes() == want
-        assert list(res.counters.cpu().numpy()) == [b * L, b * L, b, b]
+        assert list(res.counters.cpu().numpy()) == [b * L, b * L, b, b, 0, 0]
         n = int(np.prod(shape))
         y = O.bucket_bits(O.frame_message(msg[:L // 8], n, L)[1], key[:32], nonce[:16])[:n]
         assert np.array_equal(z0.cpu().numpy().reshape(-1) >= 0, y == 1)
@@ -471,7 +489,7 @@ def test_config4_sdxl_full_size(gswm, cuda_device):
     km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
     z = gswm.embed_batch(B, shape, km, 0x5EED, 0, 0, cuda_device)
     res = gswm.extract_batch(z, km)
-    assert list(res.counters.cpu().numpy()) == [B * 256, B * 256, B, B]
+    assert list(res.counters.cpu().numpy()) == [B * 256, B * 256, B, B, 0, 0]
     assert bool((res.matched == 256).all())
     # checksum of checksums: the sign pattern is the same for all latents and equals the oracle's
     y = O.bucket_bits(O.frame_message("lthero", n, 256)[1], KEY, NONCE)[:n]
@@ -482,10 +500,14 @@ def test_config4_sdxl_full_size(gswm, cuda_device):
     # sharding transparency at full size: latents [B-256, B) of the big batch == a 256-latent job at first_latent = B-256
     tail = gswm.embed_batch(256, shape, km, 0x5EED, 0, B - 256, cuda_device)
     assert torch.equal(tail, z[B - 256:])
-    sub = tail[:4].cpu().numpy().reshape(4, n)
-    for i in range(4):
+    sub = tail.cpu().numpy().reshape(256, n)
+    for i in range(256):                                    # a 256-sample subset, element by element
         ref = O.embed_gswm("lthero", KEY, NONCE, 0x5EED, 0, B - 256 + i, n, 256)
-        assert np.array_equal(sub[i] >= 0, ref >= 0) and rel_err(sub[i], ref).max() <= REL_TOL
+        assert np.array_equal(sub[i] >= 0, ref >= 0) and rel_err(sub[i], ref).max() <= REL_TOL, i
+    noisy = (tail + 1.5 * torch.randn(tail.shape, device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(4))).clamp(max=8.0)
+    rs = gswm.extract_batch(noisy, km, want_counts=True)
+    assert np.array_equal(rs.counts.cpu().numpy().astype(np.uint32),
+                          O.vote_counts_batch(noisy.cpu().numpy().reshape(256, n), KEY, NONCE, 256))
     # no two latents share their noise: |z| differs between latents (same signs, different magnitudes)
     assert not torch.equal(z[0].abs(), z[1].abs()) and not torch.equal(z[0].abs(), z[B - 1].abs())
 
@@ -493,7 +515,7 @@ def test_config4_sdxl_full_size(gswm, cuda_device):
 def test_config5_per_latent_keys_1m(gswm, cuda_device):
     """BASELINE config 5 at full size: 1 M SD-2.1 latents, each with its own key / nonce / message (RandomState(2025)),
     streamed through the device API in 8 chunks of 131 072 (8.6 GB each).  Every decoded message must equal the
-    message embedded in that latent; a 64-latent subset is checked against the oracle through `cryptography`."""
+    message embedded in that latent; a ~1024-latent subset is checked against the oracle through `cryptography`."""
     free, _ = torch.cuda.mem_get_info(cuda_device)
     total, chunk, shape, n, L = 1 << 20, 1 << 17, (4, 64, 64), 16384, 256
     if free < chunk * n * 4 + (4 << 30):
@@ -503,15 +525,15 @@ def test_config5_per_latent_keys_1m(gswm, cuda_device):
     nonces = np.frombuffer(rs.bytes(16 * total), np.uint8).reshape(total, 16)
     msgs = np.frombuffer(rs.bytes(32 * total), np.uint8).reshape(total, 32)
     out = torch.empty((chunk, *shape), dtype=torch.float32, device=cuda_device)
-    counters = torch.zeros(4, dtype=torch.int64, device=cuda_device)
+    counters = torch.zeros(gswm._lib.N_COUNTERS, dtype=torch.int64, device=cuda_device)
     for c in range(total // chunk):
         sl = slice(c * chunk, (c + 1) * chunk)
         km = gswm.KeyMaterial.make(keys[sl], nonces[sl], msgs[sl], L)
         gswm.embed_batch(chunk, shape, km, 2025, 0, c * chunk, cuda_device, out=out)
         res = gswm.extract_batch(out, km, counters=counters)
         assert torch.equal(res.messages.cpu(), torch.from_numpy(msgs[sl].copy()))
-        if c in (0, 7):
-            idx = [0, 1, chunk // 2, chunk - 1]
+        if c in (0, 7):                                     # 2 x 512 = 1024 samples through `cryptography`
+            idx = sorted({0, 1, chunk // 2, chunk - 1} | set(np.random.RandomState(c).randint(0, chunk, size=508).tolist()))
             zs = out[idx].cpu().numpy().reshape(len(idx), n)
             for j, i in enumerate(idx):
                 g = c * chunk + i
@@ -520,7 +542,7 @@ def test_config5_per_latent_keys_1m(gswm, cuda_device):
                 assert np.array_equal(zs[j] >= 0, y == 1)
                 ref = O.embed_gswm(m, k, no, 2025, 0, g, n, L)
                 assert rel_err(zs[j], ref).max() <= REL_TOL
-    assert list(counters.cpu().numpy()) == [total * L, total * L, total, total]
+    assert list(counters.cpu().numpy()) == [total * L, total * L, total, total, 0, 0]
 
 
 # ------------------------------------------------------------------------------------ host-buffer pipe
@@ -533,18 +555,18 @@ def test_host_pipe_matches_device_api(gswm, cuda_device):
     dev = gswm.embed_batch(27, (4, 64, 64), km, 5, 0, 100, cuda_device)
     assert torch.equal(out, dev.cpu())
     noisy = (out + 2.0 * torch.randn(out.shape, generator=torch.Generator().manual_seed(3)))
-    msgs, cnt, matched, counters = pipe.extract(noisy, km, want_counts=True)
+    msgs, cnt, matched, counters, flags = pipe.extract(noisy, km, want_counts=True)
     r = gswm.extract_batch(noisy.to(cuda_device), km, want_counts=True)
     assert np.array_equal(msgs, r.messages.cpu().numpy())
     assert np.array_equal(cnt, r.counts.cpu().numpy())
     assert np.array_equal(matched, r.matched.cpu().numpy())
-    assert np.array_equal(counters, r.counters.cpu().numpy())
+    assert np.array_equal(counters, r.counters.cpu().numpy()) and not flags.any()
     # fp16 host input, per-latent keys
     rs = np.random.RandomState(4)
     kmp = gswm.KeyMaterial.make(rs.bytes(32 * 27), rs.bytes(16 * 27), rs.bytes(32 * 27), 256)
     pipe.embed(out, kmp, 6)
-    m2, _, mt2, c2 = pipe.extract(out.half(), kmp)
-    assert m2.tobytes() == kmp.msgs.tobytes() and list(c2) == [27 * 256, 27 * 256, 27, 27]
+    m2, _, mt2, c2, _ = pipe.extract(out.half(), kmp)
+    assert m2.tobytes() == kmp.msgs.tobytes() and list(c2) == [27 * 256, 27 * 256, 27, 27, 0, 0]
     u = np.random.RandomState(1234).uniform(size=16384)
     zi = pipe.embed_injected(u, (4, 64, 64), km, 1, np.float64)
     assert rel_err(zi.reshape(-1), O.embed("lthero", KEY, NONCE, u, 256)).max() <= 1e-9
@@ -652,6 +674,63 @@ def test_dropin_comfy_and_webui(gswm, cuda_device, golden, golden_arrays, tmp_pa
     assert accs[0] == 1.0 and accs[2] == 1.0 and accs[1] < 1.0
 
 
+def _golden_fake_urandom():
+    """The deterministic os.urandom stand-in of the golden run (one definition: tests/golden/make_golden.py)."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    spec = importlib.util.spec_from_file_location("make_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                 # defines helpers only; main() is what touches /root/reference
+    return mod._FakeUrandom()
+
+
+def test_dropin_comfy_unseeded_batch_golden(gswm, cuda_device, golden, golden_arrays, tmp_path, monkeypatch):
+    """GSLatent with use_seed=0 (nodes.py:236-237): batch_size independent calls.  Against the reference's own run:
+    latents (numpy global stream), one info_data.txt record per latent with the widget's seed logged, and -- with an empty
+    message and key -- a fresh os.urandom message / key / nonce PER LATENT in the reference's call order."""
+    import os
+
+    from gswm import comfy_nodes as cn
+
+    monkeypatch.chdir(tmp_path)
+    g = golden["gslatent_unseeded"]
+    np.random.seed(g["np_seed"])
+    lat, first = cn.GSLatent().create_gs_latents(O.DEFAULT_KEY_HEX, O.DEFAULT_NONCE_HEX, "lthero", g["batch_size"], 0,
+                                                 g["widget_seed"], 512, 512, 256)
+    s = lat["samples"].numpy()
+    assert list(s.shape) == g["shape"] and s.dtype == np.float32 and torch.equal(first, lat["samples"][0])
+    for i in range(g["batch_size"]):
+        assert sha(np.packbits((s[i].reshape(-1) >= 0).astype(np.uint8))) == g["sha256_signs_each"][i]
+    assert rel_err(s.reshape(g["batch_size"], -1)[:, :128], golden_arrays["gslatent_unseeded_heads"]).max() <= REL_TOL
+    lines = (tmp_path / "info_data.txt").read_text().splitlines()
+    want = g["info_data_tail"]
+    assert len(lines) == len(want) == 10 * g["batch_size"]
+    for a, b in zip(lines, want):
+        assert a == b or (a.startswith("Time: ") and b.startswith("Time: "))
+    assert f"randomSeed: {g['widget_seed']}" in lines
+
+    g = golden["gslatent_unseeded_random"]
+    (tmp_path / "info_data.txt").unlink()
+    monkeypatch.setattr(os, "urandom", _golden_fake_urandom())
+    np.random.seed(g["np_seed"])
+    lat, _ = cn.GSLatent().create_gs_latents("", "", "", g["batch_size"], 0, g["widget_seed"], 256, 256, -1)
+    monkeypatch.undo()
+    monkeypatch.chdir(tmp_path)
+    s = lat["samples"].numpy()
+    assert list(s.shape) == g["shape"]
+    for i in range(g["batch_size"]):
+        assert sha(np.packbits((s[i].reshape(-1) >= 0).astype(np.uint8))) == g["sha256_signs_each"][i]
+    assert rel_err(s.reshape(g["batch_size"], -1)[:, :128], golden_arrays["gslatent_unseeded_random_heads"]).max() <= REL_TOL
+    lines = (tmp_path / "info_data.txt").read_text().splitlines()
+    want = g["info_data_tail"]
+    assert len(lines) == len(want)
+    for a, b in zip(lines, want):
+        assert a == b or (a.startswith("Time: ") and b.startswith("Time: "))
+    assert lines[1] != lines[11] and lines[3] != lines[13]          # per-latent keys and messages
+
+
 def test_argument_errors(gswm, cuda_device):
     km = gswm.KeyMaterial.make(KEY, NONCE, bytes(32), 256)
     with pytest.raises(ValueError):
@@ -660,12 +739,12 @@ def test_argument_errors(gswm, cuda_device):
         gswm.extract_batch(torch.zeros((1, 4, 96, 64), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 640))
     lib = gswm._lib.lib()
     job = gswm._lib.Job(1, 16384, 256, 0, 1, 1, 1)
-    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -7              # misaligned key pointer
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, None) == -7                  # misaligned key pointer
     job = gswm._lib.Job(1, 16384, 250, 0, 16, 16, 16)
-    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -3
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, None) == -3
     job = gswm._lib.Job(1, 1002, 32, 0, 16, 16, 16)
-    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, 16, None) == -2
-    assert lib.gswm_embed(None, 0, 0, 0, 16, 16, None) == -1
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, 16, None) == -2
+    assert lib.gswm_embed(None, 0, 0, 0, 16, None) == -1
     assert "multiple of 4" in gswm._lib.strerror(-2)
 
 
@@ -677,11 +756,11 @@ def test_empty_batches(gswm, cuda_device):
     assert tuple(z.shape) == (0, 4, 64, 64) and z.dtype == torch.float32 and z.is_cuda
     res = gswm.extract_batch(z, km, want_counts=True)
     assert tuple(res.messages.shape) == (0, 32) and tuple(res.counts.shape) == (0, 256) and tuple(res.matched.shape) == (0,)
-    assert res.counters.cpu().tolist() == [0, 0, 0, 0] and res.bit_strings() == [] and np.isnan(res.bit_accuracy())
+    assert res.counters.cpu().tolist() == [0] * 6 and res.bit_strings() == [] and np.isnan(res.bit_accuracy())
     pipe = gswm.HostPipe(cuda_device.index or 0, max_elems=16384, chunk_latents=4)
     out = pipe.embed(np.empty((0, 4, 64, 64), dtype=np.float32), km, 1)
-    msgs, cnt, matched, counters = pipe.extract(out, km, want_counts=True)
-    assert msgs.shape == (0, 32) and cnt.shape == (0, 256) and matched.shape == (0,) and counters.tolist() == [0, 0, 0, 0]
+    msgs, cnt, matched, counters, flags = pipe.extract(out, km, want_counts=True)
+    assert msgs.shape == (0, 32) and cnt.shape == (0, 256) and matched.shape == (0,) and counters.tolist() == [0] * 6 and flags.shape == (0,)
     pipe.close()
     assert gswm.launch_count() == before
     # the C ABI itself: n_latents == 0 is success, before any launch
@@ -689,7 +768,7 @@ def test_empty_batches(gswm, cuda_device):
     flat = torch.zeros(96, dtype=torch.uint8, device=cuda_device)
     buf = torch.zeros(64, dtype=torch.float32, device=cuda_device)
     job = gswm._lib.Job(0, 16384, 256, 0, flat.data_ptr(), flat.data_ptr() + 32, flat.data_ptr() + 48)
-    assert lib.gswm_embed(C.byref(job), 0, 0, 0, buf.data_ptr(), None, None) == 0
+    assert lib.gswm_embed(C.byref(job), 0, 0, 0, buf.data_ptr(), None) == 0
     assert lib.gswm_extract(C.byref(job), buf.data_ptr(), 0, flat.data_ptr(), None, None, None, None, None) == 0
     assert gswm.launch_count() == before
 
@@ -746,3 +825,310 @@ def test_large_latent_index_seed_offset_and_longest_message(gswm, cuda_device):
     assert gswm.extract_batch(zz, km).messages.cpu().numpy().tobytes() == big * 3
     with pytest.raises(gswm.GswmError):
         gswm.extract_batch(torch.zeros((1, 4, 128, 128), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 16384))
+
+
+# ------------------------------------------------------------------------------------ uniforms v3, generator pins
+def test_top_cell_refinement_matches_oracle(gswm, cuda_device):
+    """Uniforms v3: an element whose 23-bit m falls in the outermost cell (probability 2^-23) is refined by 28 more Philox
+    bits, so |z| can reach 8.21 like the reference's 53-bit uniforms.  Latents 74, 570, 746 and 2029 of seed 0x5EED each
+    hold one such element (found by scanning the oracle's integers); the kernel must reproduce the oracle there too."""
+    km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message("lthero", 32), 256)
+    n = 16384
+    for latent, elem in ((74, 6852), (570, 12884), (746, 10467), (2029, 14283)):
+        m = O.gswm_uniform_ints(0x5EED, 0, latent, n)
+        assert m[elem] == O.GSWM_TOP_CELL and (m == O.GSWM_TOP_CELL).sum() == 1
+        z = gswm.embed_batch(1, (4, 64, 64), km, 0x5EED, 0, latent, cuda_device).cpu().numpy().reshape(-1)
+        ref = O.embed_gswm("lthero", KEY, NONCE, 0x5EED, 0, latent, n, 256)
+        assert np.array_equal(z >= 0, ref >= 0) and rel_err(z, ref).max() <= REL_TOL
+        assert 5.29 < abs(ref[elem]) <= 8.21 and abs(z[elem] - ref[elem]) <= REL_TOL * abs(ref[elem])
+        # the same latent inside a large batch (persistent grid, another CTA / lane mapping) is bit-identical
+        big = gswm.embed_batch(300, (4, 64, 64), km, 0x5EED, 0, latent - 150, cuda_device)[150].cpu().numpy().reshape(-1)
+        assert np.array_equal(big, z)
+    # the refinement formula itself over its whole input range: |z| = -ndtri((m2 + 1/2) 2^-52), m2 = w >> 4
+    from scipy.special import ndtri
+    rs = np.random.RandomState(9)
+    w = np.concatenate([np.array([0, 15, 16, 0xFFFFFFFF, 0xFFFFFFF0, 0x80000000], dtype=np.uint32),
+                        rs.randint(0, 1 << 32, size=1 << 20, dtype=np.uint64).astype(np.uint32),
+                        (rs.randint(0, 1 << 16, size=1 << 16).astype(np.uint32) << np.uint32(4))])
+    d_w = torch.from_numpy(w.view(np.int32)).to(cuda_device)
+    d_o = torch.empty(w.size, dtype=torch.float32, device=cuda_device)
+    assert gswm._lib.lib().gswm_debug_top_cell(d_w.data_ptr(), w.size, d_o.data_ptr(), None) == 0
+    want = -ndtri(((w >> np.uint32(4)).astype(np.float64) + 0.5) * 2.0 ** -52)
+    got = d_o.cpu().numpy()
+    assert rel_err(got, want).max() <= 5e-7
+    assert got.max() <= 8.2096 and got.min() >= 5.2947          # [norm.ppf(1 - 2^-24), norm.ppf(1 - 2^-53)]
+
+
+def test_philox4x32_known_answers(gswm, cuda_device):
+    """The generator core against PUBLISHED vectors: Random123's kat_vectors for philox4x32-10 (the same kernel code runs
+    7 rounds in the product), plus the 7-round form against the oracle's restatement on random inputs."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    lib = gswm._lib.lib()
+    inp = np.array([list(c) + list(k) for c, k, _ in kat], dtype=np.uint32)
+    d_in = torch.from_numpy(inp.view(np.int32)).to(cuda_device)
+    d_out = torch.empty((len(kat), 4), dtype=torch.int32, device=cuda_device)
+    assert lib.gswm_debug_philox4x32(d_in.data_ptr(), len(kat), 10, d_out.data_ptr(), None) == 0
+    got = d_out.cpu().numpy().view(np.uint32)
+    for i, (_, _, want) in enumerate(kat):
+        assert tuple(int(x) for x in got[i]) == want
+    rs = np.random.RandomState(123)
+    rnd = rs.randint(0, 1 << 32, size=(4096, 6), dtype=np.uint64).astype(np.uint32)
+    d_in = torch.from_numpy(rnd.view(np.int32)).to(cuda_device)
+    d_out = torch.empty((4096, 4), dtype=torch.int32, device=cuda_device)
+    for rounds in (7, 10):
+        assert lib.gswm_debug_philox4x32(d_in.data_ptr(), 4096, rounds, d_out.data_ptr(), None) == 0
+        got = d_out.cpu().numpy().view(np.uint32)
+        for i in range(0, 4096, 257):
+            want = O.philox4x32(rnd[i:i + 1, :4], (int(rnd[i, 4]), int(rnd[i, 5])), rounds)[0]
+            assert np.array_equal(got[i], want), (rounds, i)
+    assert lib.gswm_philox_rounds() == 7
+
+
+def test_mt19937_stream_is_numpys(gswm, cuda_device):
+    """The device MT19937 against numpy itself (the reference's generator, nodes.py:52-53): RandomState(seed).uniform,
+    bit for bit -- > 10^6 consecutive draws (1600+ state regenerations), every position around the 624-word block
+    boundaries, extreme seeds, many streams in one launch."""
+    u = gswm.mt19937_uniform(42, 1_100_003, device=cuda_device).cpu().numpy()[0]
+    want = np.random.RandomState(42).uniform(0, 1, size=u.size)
+    assert u.dtype == np.float64 and np.array_equal(u, want)
+    assert np.array_equal(u[300:330], want[300:330]) and np.array_equal(u[620:640], want[620:640])   # 312-double regeneration edges
+    for seed in (0, 1, 58, 2 ** 31, 2 ** 32 - 1):
+        for n in (1, 2, 311, 312, 313, 623, 624, 625, 1000):
+            got = gswm.mt19937_uniform(seed, n, device=cuda_device).cpu().numpy()[0]
+            assert np.array_equal(got, np.random.RandomState(seed).uniform(size=n)), (seed, n)
+    seeds = np.random.RandomState(3).randint(0, 2 ** 32, size=200, dtype=np.uint64)
+    got = gswm.mt19937_uniform(seeds, 5000, device=cuda_device).cpu().numpy()
+    for i in (0, 1, 57, 199):
+        assert np.array_equal(got[i], np.random.RandomState(int(seeds[i])).uniform(size=5000))
+    got = gswm.mt19937_uniform(1000, 700, n_streams=3, device=cuda_device).cpu().numpy()       # one int: stream s uses seed + s
+    for s_ in range(3):
+        assert np.array_equal(got[s_], np.random.RandomState(1000 + s_).uniform(size=700))
+    with pytest.raises(ValueError):
+        gswm.mt19937_uniform(2 ** 32, 10, device=cuda_device)                                   # numpy raises ValueError too
+
+
+def test_embed_mt19937_is_the_seeded_reference(gswm, cuda_device, golden, golden_arrays):
+    """gswm_embed_mt19937: the reference's seeded embed with nothing uploaded.  Against the reference's own seeded runs
+    (ComfyUI node, all shapes incl. multi-tile and ragged ones) and against the injected-uniform path fed numpy's stream."""
+    for c in golden["embed_comfy"]:
+        n = 4 * (c["width"] // 8) * (c["height"] // 8)
+        L = c["message_length"] if c["message_length"] != -1 else gswm.choose_watermark_length(n)
+        km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message(c["message"], L // 8), L)
+        shape = (4, c["height"] // 8, c["width"] // 8)
+        z = gswm.embed_batch_mt19937(c["seed"], 1, shape, km, torch.float32, cuda_device).cpu().numpy().reshape(-1)
+        assert sha(np.packbits((z >= 0).astype(np.uint8))) == c["sha256_signs"], c["name"]
+        assert rel_err(z[:256], golden_arrays[c["name"] + "_z32_head"]).max() <= REL_TOL, c["name"]
+        u = torch.from_numpy(np.random.RandomState(c["seed"]).uniform(size=n)).to(cuda_device)
+        zi = gswm.embed_batch_injected(u, shape, km, 1, torch.float32).cpu().numpy().reshape(-1)
+        assert np.array_equal(z, zi), c["name"]                  # same uniforms, same arithmetic: bit-identical
+    # a batch with one seed per latent and per-latent keys, float64 out
+    rs = np.random.RandomState(12)
+    b, shape, n, L = 9, (4, 64, 64), 16384, 256
+    seeds = rs.randint(0, 2 ** 32, size=b, dtype=np.uint64)
+    keys, nonces, msgs = rs.bytes(32 * b), rs.bytes(16 * b), rs.bytes(32 * b)
+    km = gswm.KeyMaterial.make(keys, nonces, msgs, L)
+    z = gswm.embed_batch_mt19937(seeds, b, shape, km, torch.float64, cuda_device).cpu().numpy().reshape(b, n)
+    for i in range(b):
+        ref = O.embed(msgs[32 * i:32 * i + 32], keys[32 * i:32 * i + 32], nonces[16 * i:16 * i + 16],
+                      np.random.RandomState(int(seeds[i])).uniform(size=n), L)
+        assert np.array_equal(z[i] >= 0, ref >= 0) and rel_err(z[i], ref).max() <= 1e-9
+
+
+# ------------------------------------------------------------------------------------ reference error conditions in K3
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.float64])
+def test_extract_flags_inputs_the_reference_rejects(gswm, cuda_device, golden, dtype):
+    """extract.py:83 raises on a NaN (int(nan)), extract.py:86 on any element >= 8.292361075813597 (digit '2').  The extract
+    kernel finds both in its one pass: per-latent flags, two counters; everything else about those latents is unchanged."""
+    lib = gswm._lib
+    km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message("lthero", 32), 256)
+    b, n = 40, 16384
+    z = gswm.embed_batch(b, (4, 64, 64), km, 5, 0, 0, cuda_device).reshape(b, n).to(dtype)
+    clean = gswm.extract_batch(z.clone(), km, want_counts=True)
+    assert not clean.flags.any() and clean.counters.cpu().tolist()[4:] == [0, 0]
+    big = {torch.float32: 8.29236125946045, torch.float16: 8.296875, torch.bfloat16: 8.3125, torch.float64: 8.292361075813597}[dtype]
+    ok = {torch.float32: 8.292360305786133, torch.float16: 8.2890625, torch.bfloat16: 8.25, torch.float64: 8.292361075813595}[dtype]
+    from scipy.stats import norm
+    assert int(norm.cdf(big) * 2) == 2 and int(norm.cdf(ok) * 2) == 1            # the type's first rejected / last accepted value
+    want = np.zeros(b, dtype=np.uint8)
+    plan = {1: (0, float("nan")), 2: (n - 1, float("nan")), 3: (7777, -float("nan")), 5: (0, big), 6: (n - 1, float("inf")),
+            7: (12345, 9.0), 8: (100, ok), 9: (200, -float("inf")), 10: (300, -9.0), 11: (5, float("nan")), 12: (8191, big),
+            13: (8192, big), 39: (16383, float("nan"))}
+    for row, (col, val) in plan.items():
+        z[row, col] = val
+        want[row] = lib.FLAG_NAN if val != val else (lib.FLAG_RANGE if val >= big else 0)
+    z[11, 9] = big                                                             # NaN and an oversized value: NaN wins (it raises first)
+    res = gswm.extract_batch(z, km, want_counts=True)
+    assert np.array_equal(res.flags.cpu().numpy(), want)
+    c = res.counters.cpu().tolist()
+    assert c[4] == int((want == lib.FLAG_NAN).sum()) and c[5] == int((want == lib.FLAG_RANGE).sum()) and c[3] == b
+    # the oracle (= the reference) raises exactly for the flagged rows, and agrees on the counts of all the others
+    zh = z.double().cpu().numpy() if dtype == torch.float64 else z.float().cpu().numpy()
+    for i in range(b):
+        if want[i]:
+            with pytest.raises(ValueError):
+                O.vote_counts(zh[i], KEY, NONCE, 256)
+        else:
+            assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(zh[i], KEY, NONCE, 256))
+    # the golden cases through the two front-ends
+    import io
+    from gswm import extract as gx
+    args = types.SimpleNamespace(key=KEY, nonce=NONCE, l=1, message_length=256, original_message_hex=(b"lthero" + bytes(26)).hex())
+    for bad in golden["quantise_raises"]:
+        t = z[0].clone().reshape(1, 4, 64, 64)
+        t[0, 0, 0, 0] = float(bad["z"])
+        if dtype != torch.float64 and float(bad["z"]) == 8.292361075813597:
+            continue                                                            # not representable in the narrower types
+        with pytest.raises(ValueError):
+            gx.recover_exactracted_message(t.cpu(), args)
+    buf = io.StringIO()
+    strings, accs, avg = gx.evaluate_latents([f"img{i}.png" for i in range(b)], z.cpu(), args, buf)
+    text = buf.getvalue()
+    for i in range(b):
+        if want[i]:
+            assert strings[i] is None and accs[i] is None and f"Error processing img{i}.png: " in text
+        else:
+            assert accs[i] == 1.0 and f"img{i}.png, Bit Accuracy, 1.0" in text
+    assert avg == 1.0 and "Average Bit Accuracy, 1.0" in text
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("shape,L", [((4, 8, 16), 8), ((4, 8, 16), 4), ((4, 8, 16), 1), ((4, 8, 16), 2), ((4, 8, 16), 16),
+                                     ((4, 6, 8), 12), ((4, 6, 8), 24), ((4, 10, 10), 100), ((4, 64, 64), 8), ((4, 64, 64), 20480 // 5),
+                                     ((4, 96, 64), 24), ((4, 64, 64), 16), ((4, 64, 64), 16384 // 4), ((4, 72, 72), 81)])
+def test_extract_any_message_length(gswm, cuda_device, dtype, shape, L):
+    """extract.py:195 `--message_length` is an arbitrary integer: any length that divides the latent decodes (segments of
+    L bits, extract.py:91-98), not only multiples of 32.  Counts, messages (rows of ceil(L/8) bytes, unused low bits zero)
+    and matched bits against the oracle."""
+    n = int(np.prod(shape))
+    assert n % L == 0
+    rs = np.random.RandomState(n * 31 + L)
+    b = 5
+    zn = torch.from_numpy(rs.standard_normal((b, *shape)).astype(np.float32)).to(dtype)
+    ref_msg = rs.bytes((L + 7) // 8)
+    km = gswm.KeyMaterial.make(KEY, NONCE, ref_msg, L)
+    res = gswm.extract_batch(zn.to(cuda_device), km, want_counts=True)
+    zh = zn.float().numpy()
+    ref_bits = np.unpackbits(np.frombuffer(ref_msg, np.uint8))[:L]
+    total = 0
+    for i in range(b):
+        assert np.array_equal(res.counts[i].cpu().numpy().astype(np.uint32), O.vote_counts(zh[i], KEY, NONCE, L)), i
+        bits = O.recover_message_bits(zh[i], KEY, NONCE, L)
+        assert O.bits_to_bytes(bits) == res.messages[i].cpu().numpy().tobytes()
+        assert res.bit_strings()[i] == O.recover_message(zh[i], KEY, NONCE, L)
+        m = int((bits == ref_bits).sum())
+        assert int(res.matched[i]) == m
+        total += m
+    assert res.counters.cpu().tolist() == [total, b * L, int((res.matched == L).sum()), b, 0, 0]
+    # the reference-named function with the same length
+    from gswm import extract as gx
+    args = types.SimpleNamespace(key=KEY, nonce=NONCE, l=1, message_length=L)
+    assert gx.recover_exactracted_message(zn[:1], args) == O.recover_message(zh[0], KEY, NONCE, L)
+    with pytest.raises(IndexError):
+        gx.recover_exactracted_message(zn[:1], types.SimpleNamespace(key=KEY, nonce=NONCE, l=1, message_length=n - 1))
+
+
+def test_keys_in_flight_flag_changes_nothing_but_the_ordering(gswm, cuda_device):
+    """GSWM_JOB_KEYS_IN_FLIGHT moves every key-material read behind the grid dependency wait (for callers whose key
+    material is produced by a programmatic-launch kernel just ahead in the stream).  Same results, both kernels, both
+    key modes -- with the key material written by a device kernel (torch copy) immediately before each launch."""
+    import ctypes as C
+    lib = gswm._lib.lib()
+    rs = np.random.RandomState(6)
+    for per in (0, 1):
+        b, n, L = 300, 16384, 256
+        rows = b if per else 1
+        src = torch.from_numpy(np.frombuffer(rs.bytes(80 * rows), np.uint8).copy()).to(cuda_device)
+        flat = torch.zeros_like(src)
+        outs = []
+        for flag in (0, gswm._lib.JOB_KEYS_IN_FLIGHT):
+            z = torch.empty((b, n), dtype=torch.float32, device=cuda_device)
+            msgs = torch.empty((b, 32), dtype=torch.uint8, device=cuda_device)
+            ctr = torch.zeros(6, dtype=torch.int64, device=cuda_device)
+            job = gswm._lib.Job(b, n, L, per | flag, flat.data_ptr(), flat.data_ptr() + 32 * rows, flat.data_ptr() + 48 * rows)
+            sp = torch.cuda.current_stream().cuda_stream
+            for _ in range(3):                                   # back to back: embed, extract, embed, extract, ...
+                flat.zero_()
+                flat.copy_(src)                                  # key material lands just ahead of the launches
+                assert lib.gswm_embed(C.byref(job), 9, 0, 0, z.data_ptr(), sp) == 0
+                assert lib.gswm_extract(C.byref(job), z.data_ptr(), 0, msgs.data_ptr(), None, None, None, ctr.data_ptr(), sp) == 0
+            outs.append((z.clone(), msgs.clone(), ctr.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+        assert outs[0][2].tolist() == [3 * b * L, 3 * b * L, 3 * b, 3 * b, 0, 0]
+        want = src[48 * rows:].cpu().numpy().tobytes()
+        assert outs[0][1].cpu().numpy().tobytes() == (want if per else want * b)
+
+
+# ------------------------------------------------------------------------------------ multi-GPU exchange (one GPU is enough to run it)
+def test_comm_allreduce_two_ranks_on_one_device(gswm, cuda_device):
+    """gswm_comm with both ranks in this process (gswm_comm_connect_local) and on this one GPU: the mailbox exchange is
+    the same code that runs over NVLink -- stores into the peer's mailbox, release flag, acquire spin, sum.  The two
+    ranks' kernels run concurrently on two streams.  Stand-alone all-reduce, then the form fused into the extract
+    kernel, several epochs (the mailboxes are double-buffered by epoch parity)."""
+    import ctypes as C
+    lib = gswm._lib.lib()
+    dev = cuda_device.index or 0
+    hs = [C.c_void_p(), C.c_void_p()]
+    for r in range(2):
+        assert lib.gswm_comm_create(C.byref(hs[r]), dev, r, 2, None) == 0
+    arr = (C.c_void_p * 2)(hs[0], hs[1])
+    assert lib.gswm_comm_connect_local(arr, 2) == 0
+    streams = [torch.cuda.Stream(cuda_device), torch.cuda.Stream(cuda_device)]
+    bufs = [torch.zeros(6, dtype=torch.int64, device=cuda_device) for _ in range(2)]
+    for epoch in range(5):
+        vals = [[10 * epoch + r + i for i in range(6)] for r in range(2)]
+        for r in range(2):
+            bufs[r].copy_(torch.tensor(vals[r], dtype=torch.int64))
+        torch.cuda.synchronize()
+        for r in range(2):
+            assert lib.gswm_comm_allreduce_counters(hs[r], bufs[r].data_ptr(), 6, streams[r].cuda_stream) == 0
+        torch.cuda.synchronize()
+        want = [vals[0][i] + vals[1][i] for i in range(6)]
+        assert bufs[0].tolist() == want and bufs[1].tolist() == want
+        assert lib.gswm_comm_status(hs[0]) == 0 and lib.gswm_comm_status(hs[1]) == 0
+    # fused into K3: rank r decodes its own shard; each rank's `reduced` holds the sum of both ranks' ACCUMULATED counters
+    msg = gswm.pad_message("lthero", 32)
+    km = gswm.KeyMaterial.make(KEY, NONCE, msg, 256)
+    from gswm.codec import _DeviceJob
+    shards = [(0, 700), (700, 1000)]
+    zs = [gswm.embed_batch(hi - lo, (4, 64, 64), km, 3, 0, lo, cuda_device) for lo, hi in shards]
+    zs[1][5, 0, 0, 0] = float("nan")                                # one rejected latent on rank 1
+    ctrs = [torch.zeros(6, dtype=torch.int64, device=cuda_device) for _ in range(2)]
+    reds = [torch.full((6,), -1, dtype=torch.int64, device=cuda_device) for _ in range(2)]
+    outs = [torch.empty((hi - lo, 32), dtype=torch.uint8, device=cuda_device) for lo, hi in shards]
+    jobs = [_DeviceJob(km, hi - lo, 16384, cuda_device) for lo, hi in shards]
+    torch.cuda.synchronize()
+    for step in range(3):
+        for r in range(2):
+            if step < 2:                                          # plain launches accumulate ...
+                rc = lib.gswm_extract(C.byref(jobs[r].job), zs[r].data_ptr(), 0, outs[r].data_ptr(), None, None, None,
+                                      ctrs[r].data_ptr(), streams[r].cuda_stream)
+            else:                                                 # ... the last one carries the exchange
+                rc = lib.gswm_extract_allreduce(C.byref(jobs[r].job), zs[r].data_ptr(), 0, outs[r].data_ptr(), None, None, None,
+                                                ctrs[r].data_ptr(), hs[r], reds[r].data_ptr(), streams[r].cuda_stream)
+            assert rc == 0
+    torch.cuda.synchronize()
+    assert ctrs[0].tolist() == [3 * 700 * 256, 3 * 700 * 256, 3 * 700, 3 * 700, 0, 0]
+    assert ctrs[1].tolist()[1:] == [3 * 300 * 256, 3 * 299, 3 * 300, 3, 0]
+    want = (ctrs[0] + ctrs[1]).tolist()
+    assert reds[0].tolist() == want and reds[1].tolist() == want
+    assert lib.gswm_comm_status(hs[0]) == 0
+    # argument errors do not consume an epoch (the ranks would fall out of step)
+    bad = gswm._lib.Job(1, 16384, 640, 0, 16, 16, None)
+    assert lib.gswm_extract_allreduce(C.byref(bad), zs[0].data_ptr(), 0, outs[0].data_ptr(), None, None, None, ctrs[0].data_ptr(),
+                                      hs[0], reds[0].data_ptr(), None) == -3
+    for r in range(2):
+        assert lib.gswm_comm_allreduce_counters(hs[r], bufs[r].data_ptr(), 6, streams[r].cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert bufs[0].tolist() == bufs[1].tolist() and lib.gswm_comm_status(hs[1]) == 0      # still in step
+    for h in hs:
+        lib.gswm_comm_destroy(h)
+    # a one-rank communicator is its own peer: the Python wrapper outside torch.distributed
+    comm = gswm.Comm(cuda_device)
+    t = torch.arange(6, dtype=torch.int64, device=cuda_device)
+    assert comm.allreduce_counters(t).tolist() == [0, 1, 2, 3, 4, 5] and comm.status() == 0
+    res = gswm.extract_batch(zs[0], km, comm=comm)
+    assert res.reduced.tolist() == res.counters.tolist() == [700 * 256, 700 * 256, 700, 700, 0, 0]
+    comm.close()

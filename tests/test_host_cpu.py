@@ -25,7 +25,6 @@ def gswm():
 def test_library_exports_every_declared_symbol(gswm):
     header = open(os.path.join(ROOT, "include", "gswm.h")).read()
     declared = set(re.findall(r"\b(gswm_[a-z0-9_]+)\s*\(", header))
-    declared -= {"gswm_workspace_bytes()", }
     assert {"gswm_embed", "gswm_extract", "gswm_chacha20_keystream", "gswm_pipe_extract"} <= declared
     lib = gswm._lib.lib()
     for name in sorted(declared):
@@ -43,26 +42,38 @@ def test_library_is_sm100a(gswm):
 
 def test_abi_basics_without_gpu(gswm):
     lib = gswm._lib.lib()
-    assert lib.gswm_abi_version() == 1
+    assert lib.gswm_abi_version() == 2 == gswm._lib.ABI_VERSION
     assert gswm._lib.strerror(0) == "success"
     for code in range(-7, 0):
         assert gswm._lib.strerror(code).startswith("gswm:")
-    job = gswm._lib.Job(3, 16384, 256, 0, None, None, None)
-    assert lib.gswm_workspace_bytes(C.byref(job)) == 0                  # keystream lives in shared memory only
-    job.per_latent = 1
-    assert lib.gswm_workspace_bytes(C.byref(job)) == 0
+    assert "4-byte" in gswm._lib.strerror(-7) and "16-byte" in gswm._lib.strerror(-7)    # both alignment rules are named
+    assert not hasattr(lib, "gswm_workspace_bytes")                    # ABI v1's reserved scratch-memory plumbing is gone
     # argument validation happens before any CUDA call
-    assert lib.gswm_embed(None, 0, 0, 0, None, None, None) == -1
+    assert lib.gswm_embed(None, 0, 0, 0, None, None) == -1
     bad = gswm._lib.Job(1, 1002, 32, 0, 16, 16, 16)
-    assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, 16, None) == -2
+    assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, None) == -2
     bad = gswm._lib.Job(1, 16384, 48, 0, 16, 16, 16)
-    assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, 16, None) == -3
+    assert lib.gswm_embed(C.byref(bad), 0, 0, 0, 16, None) == -3        # embed: multiples of 32 only
+    assert lib.gswm_embed_mt19937(C.byref(bad), None, 1, 16, 0, None) == -3
+    ok = gswm._lib.Job(1, 16384, 256, 0, 16, 16, 16)
+    assert lib.gswm_embed(C.byref(ok), 0, 0, -5, 16, None) == -5        # negative global latent index
+    assert lib.gswm_embed(C.byref(ok), 0, 1 << 62, 0, 16, None) == -5   # offset >= 2^62
     bad = gswm._lib.Job(1, 16384, 640, 0, 16, 16, 16)           # 640 does not divide 16384
     assert lib.gswm_extract(C.byref(bad), 16, 0, 16, None, None, None, 16, None) == -3
-    ok = gswm._lib.Job(1, 16384, 256, 0, 16, 16, 16)
     assert lib.gswm_extract(C.byref(ok), 16, 7, 16, None, None, None, 16, None) == -4
     assert lib.gswm_extract(C.byref(ok), 8, 0, 16, None, None, None, 16, None) == -7
+    odd = gswm._lib.Job(1, 36, 12, 0, 16, 16, None)             # 36 fp16 elements = 72-byte rows: not fetchable in 16-byte pieces
+    assert lib.gswm_extract(C.byref(odd), 16, 1, 16, None, None, None, 16, None) == -7
+    big = gswm._lib.Job(1, 1 << 20, 1 << 14, 0, 16, 16, None)   # messages longer than 8192 bits
+    assert lib.gswm_extract(C.byref(big), 16, 0, 16, None, None, None, 16, None) == -5
     assert lib.gswm_chacha20_keystream(16, 16, 1, 100, 16, None) == -2
+    assert lib.gswm_debug_philox4x32(16, 4, 8, 16, None) == -5        # 7 or 10 rounds
+    # communicator entry points
+    h = C.c_void_p()
+    assert lib.gswm_comm_create(C.byref(h), 0, 3, 2, None) == gswm._lib.E_COMM       # rank outside [0, n_ranks)
+    assert lib.gswm_comm_create(C.byref(h), 0, 0, 33, None) == gswm._lib.E_COMM      # more than GSWM_COMM_MAX_RANKS
+    assert lib.gswm_comm_allreduce_counters(None, 16, 4, None) == -1
+    assert lib.gswm_allreduce_counters(None, 16, 4, None) == -1
 
 
 def test_header_is_plain_c_and_links_from_c(gswm, tmp_path):
@@ -266,6 +277,48 @@ def test_comfy_nodes_interface_without_comfyui(gswm, monkeypatch):
     node.sample("m", "disable", "disable", 7, 20, 8.0, "euler", "normal", "p", "n", empty, gs, 0, 10000, "enable")
     assert torch.equal(calls["noise"], torch.zeros(2, 4, 8, 8)) and calls["noise"].device.type == "cpu"
     assert calls["kw"]["disable_noise"] is True
+
+
+def test_comfy_unseeded_batch_host_logic_follows_the_reference(gswm, golden, monkeypatch, tmp_path):
+    """Host side of GSLatent(use_seed=0) without a GPU: the device call is replaced by a recorder.  Per latent -- as the
+    reference's batch_size sequential calls do (nodes.py:236-237) -- a fresh os.urandom message / key / nonce when the
+    widgets are empty, its own info_data.txt record, and the widget's seed in the log (nodes.py:131,134)."""
+    import importlib.util
+    import os
+
+    import torch
+
+    from gswm import _embed_common as common
+    from gswm import comfy_nodes as cn
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    seen = {}
+
+    def fake_embed(u, latent_shape, key, nonce, k, msg_bits, n_latents, out_dtype, device=None):
+        seen.update(u=u, shape=latent_shape, key=key, nonce=nonce, k=k, bits=msg_bits, n=n_latents)
+        return torch.zeros((n_latents, *latent_shape), dtype=out_dtype)
+
+    monkeypatch.setattr(common, "embed_injected", fake_embed)
+    monkeypatch.chdir(tmp_path)
+    g = golden["gslatent_unseeded_random"]
+    monkeypatch.setattr(os, "urandom", mg._FakeUrandom())
+    np.random.seed(g["np_seed"])
+    lat, first = cn.GSLatent().create_gs_latents("", "", "", g["batch_size"], 0, g["widget_seed"], 256, 256, -1)
+    assert list(lat["samples"].shape) == g["shape"] and seen["bits"] == 128 and seen["n"] == 2
+    assert len(seen["key"]) == 64 and len(seen["nonce"]) == 32 and len(seen["k"]) == 32      # one row per latent
+    assert np.array_equal(seen["u"], np.random.RandomState(g["np_seed"]).uniform(size=(2, 4096)))
+    lines = (tmp_path / "info_data.txt").read_text().splitlines()
+    want = g["info_data_tail"]
+    assert [a for a in lines if not a.startswith("Time: ")] == [b for b in want if not b.startswith("Time: ")]
+    # nothing random: one shared row, still one record per latent
+    (tmp_path / "info_data.txt").unlink()
+    g = golden["gslatent_unseeded"]
+    cn.GSLatent().create_gs_latents(gswm.DEFAULT_KEY_HEX, gswm.DEFAULT_NONCE_HEX, "lthero", 3, 0, 77, 512, 512, 256)
+    assert len(seen["key"]) == 32 and len(seen["k"]) == 32 and seen["n"] == 3
+    lines = (tmp_path / "info_data.txt").read_text().splitlines()
+    assert [a for a in lines if not a.startswith("Time: ")] == [b for b in g["info_data_tail"] if not b.startswith("Time: ")]
 
 
 def test_webui_scripts_patch_and_restore_with_stub_webui(gswm, monkeypatch):

@@ -176,11 +176,38 @@ def main():
         return rel.max()
 
     report(m_all, "samples   ")
-    if args.exhaustive:
-        worst = 0.0
-        for lo in range(0, 1 << 23, 1 << 20):
-            worst = max(worst, report(np.arange(lo, lo + (1 << 20), dtype=np.uint32), f"m>>20=={lo >> 20}"))
-        print("exhaustive worst relative error:", worst)
+
+    # The kernel enters its rare tail-patch block on an INTEGER test that is evaluated before the MUFU: some element of the
+    # float4 has bits(f) > FGUARD_BITS.  It must never miss an element with X < X_SPLIT, so the guard sits 64 grid points
+    # below the first m whose emulated X falls under X_SPLIT (X moves 1.4e-4 per grid point there, MUFU.LG2's error is
+    # ~2e-7), and the implication is checked over all 2^23 values of m.
+    m_every = np.arange(1 << 23, dtype=np.uint32)
+    _, _, X_every = kernel_arith(m_every, c_shift)
+    m_first_tail = int(m_every[X_every < X_SPLIT].min())
+    m_guard = m_first_tail - 64
+    assert (X_every[:m_guard + 1] >= X_SPLIT).all() and (X_every[m_first_tail + 64:] < X_SPLIT).all()
+    print(f"integer guard: first tail m={m_first_tail}, guard m={m_guard} (fbits 0x{0x3F800000 | m_guard:08X}); "
+          f"X(2^23-1)={float(X_every[-1])!r}, X(2^23-2)={float(X_every[-2])!r}")
+
+    # ---- the outermost grid cell, refined (uniforms v3): m = 2^23 - 1 is subdivided by a 28-bit m2, p = P(|Z| > z) / 2 =
+    # (m2 + 1/2) 2^-52, z in [5.29, 8.21].  Kernel arithmetic: mf = float(m2) + 0.5f; s = sqrt(52 - lg2(mf)); z = R(s - S1).
+    m2 = np.unique(np.concatenate([np.arange(0, 70000), (1 << 28) - 1 - np.arange(0, 70000),
+                                   np.random.RandomState(28).randint(0, 1 << 28, size=300000),
+                                   np.logspace(0, 8.42, 100000).astype(np.int64)]))
+    m2 = m2[m2 < (1 << 28)]
+    z_far = -ndtri((m2.astype(np.float64) + 0.5) * 2.0 ** -52)
+    s_far = np.sqrt(52.0 - np.log2(m2 + 0.5))
+    f_lo, f_hi = s_far.min() - 1e-3, s_far.max() + 1e-3
+    S1 = float(np.float32(0.5 * (f_lo + f_hi)))
+    o = np.argsort(s_far)
+    cf, e_f = lawson_fit(s_far[o] - S1, z_far[o], 5, f_lo - S1, f_hi - S1)
+    mf = (m2.astype(np.float32) + np.float32(0.5)).astype(np.float32)
+    s32 = np.sqrt((np.float32(52.0) - np.log2(mf.astype(np.float64)).astype(np.float32)).astype(np.float64)).astype(np.float32)
+    z32 = horner32(cf, (s32.astype(np.float64) - S1).astype(np.float32))
+    e_far = (np.abs(z32.astype(np.float64) - z_far) / z_far).max()
+    print(f"refined outermost cell (degree 5 in sqrt(52 - lg2 m2)): fit error {e_f:.3e}, emulated fp32 max rel err {e_far:.3e}, "
+          f"z in [{z_far.min():.4f}, {z_far.max():.4f}]")
+    assert e_far < 5e-7
 
     # ---- float64 path (injected-uniform mode): same structure in w = -ln(t*(2-t)), natural log ----
     # samples are (v, t) pairs with t = 1 - v exact in float64
@@ -223,9 +250,12 @@ def main():
             fo.write(f"#define GSWM_HNQ_CSHIFT {c_shift!r}f\n")
             fo.write(f"#define GSWM_HNQ_XSPLIT {float(X_SPLIT)!r}f\n")
             fo.write(f"#define GSWM_HNQ_S0 {S0!r}f\n")
+            fo.write(f"#define GSWM_HNQ_FGUARD_BITS 0x{0x3F800000 | m_guard:08X}u   // X < XSPLIT  =>  bits(f) > this  (m > {m_guard})\n")
             fo.write("// highest power first\n")
             fo.write("#define GSWM_HNQ_CENTRAL_COEFFS " + ", ".join(f"{float(np.float32(c))!r}f" for c in cc) + "\n")
             fo.write("#define GSWM_HNQ_TAIL_COEFFS " + ", ".join(f"{float(np.float32(c))!r}f" for c in ct) + "\n")
+            fo.write(f"#define GSWM_HNQ_S1 {S1!r}f\n")
+            fo.write("#define GSWM_HNQ_FARTAIL_COEFFS " + ", ".join(f"{float(np.float32(c))!r}f" for c in cf) + "\n")
             fo.write("// float64 path: g = v*Pc(w - WSPLIT/2) | Qa(sqrt(w) - SA0) | Qb(sqrt(w) - SB0),  w = -ln(t*(2-t))\n")
             fo.write(f"#define GSWM_HNQ64_WSPLIT {W_SPLIT!r}\n#define GSWM_HNQ64_WA {WA!r}\n")
             fo.write(f"#define GSWM_HNQ64_SA0 {float(SA0)!r}\n#define GSWM_HNQ64_SB0 {float(SB0)!r}\n")

@@ -19,9 +19,7 @@ def load(path):
     L = C.CDLL(path)
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     JP = C.POINTER(_lib.Job)
-    L.gswm_workspace_bytes.restype = C.c_size_t
-    L.gswm_workspace_bytes.argtypes = [JP]
-    L.gswm_embed.argtypes = [JP, u64, u64, i64, vp, vp, vp]
+    L.gswm_embed.argtypes = [JP, u64, u64, i64, vp, vp]
     L.gswm_extract.argtypes = [JP, vp, i32, vp, vp, vp, vp, vp, vp]
     return L
 
@@ -47,21 +45,18 @@ def main():
     zn = torch.empty((B, n), dtype=zdt, device=dev)
     msgs = torch.empty((B, 32), dtype=torch.uint8, device=dev)
     matched = torch.empty((B,), dtype=torch.int32, device=dev)
-    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    counters = torch.zeros(6, dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     reps = int(os.environ.get("KB_REPS", 200))
     for path in sys.argv[1:]:
         L = load(path)
-        ws = torch.empty(max(16, L.gswm_workspace_bytes(C.byref(job))), dtype=torch.uint8, device=dev)
-        ws2 = torch.empty_like(ws)
-
         def embed():
-            rc = L.gswm_embed(C.byref(job), 0x5EED, 0, 0, z.data_ptr(), ws.data_ptr(), st)
+            rc = L.gswm_embed(C.byref(job), 0x5EED, 0, 0, z.data_ptr(), st)
             assert rc == 0, rc
 
         def extract():
-            rc = L.gswm_extract(C.byref(job), zn.data_ptr(), zcode, msgs.data_ptr(), None, matched.data_ptr(), counters.data_ptr(),
-                                ws2.data_ptr(), st)
+            rc = L.gswm_extract(C.byref(job), zn.data_ptr(), zcode, msgs.data_ptr(), None, matched.data_ptr(), None,
+                                counters.data_ptr(), st)
             assert rc == 0, rc
 
         embed()
