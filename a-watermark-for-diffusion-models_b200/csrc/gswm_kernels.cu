@@ -109,8 +109,12 @@ __device__ __forceinline__ void build_sign_lut(float4* lut) {
 }
 
 #ifndef GSWM_TOPCELL
-#define GSWM_TOPCELL 1
+#define GSWM_TOPCELL 1      // 1: the outermost grid cell is refined (uniforms v3); 0: diagnostic build without (the cell's midpoint)
 #endif
+struct TopCellShared {      // the CTA's log of outermost-cell elements (gswm_math.cuh: TopCellLog)
+  float* list[kTopCellSlots];
+  uint32_t count;
+};
 #ifndef GSWM_PHILOX_CONST_KEYS
 #define GSWM_PHILOX_CONST_KEYS 1
 #endif
@@ -122,7 +126,8 @@ __device__ __forceinline__ void build_sign_lut(float4* lut) {
 template <bool kGuard, bool kHoisted = false>
 __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const uint8_t* __restrict__ s_bytes,
                                                       const float4* __restrict__ my_sign, float4* __restrict__ out4,
-                                                      uint64_t g_tile, uint32_t sidx, uint32_t n_f4, uint32_t sign_pack = 0) {
+                                                      uint64_t g_tile, uint32_t sidx, uint32_t n_f4, TopCellShared* s_top,
+                                                      uint32_t sign_pack = 0) {
   const uint64_t g = g_tile + (uint64_t)sidx * kThreads;
   const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
 #if GSWM_PHILOX_CONST_KEYS
@@ -149,9 +154,9 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
                                                                     __byte_perm(sign_pack, 0u, 0x4440u | k))
                                 : my_sign[2u * s_bytes[i >> 1]];
 #endif
-    // uniforms v3: an element in the outermost grid cell draws its refinement from Philox call 3 of this counter, key word 1 + k
+    // uniforms v3: an element in the outermost grid cell is logged here and refined in the kernel's epilogue
 #if GSWM_TOPCELL
-    const TopCellRefine top{g_tile, sidx * kThreads, a.off_lo, a.off_hi, a.seed_lo, a.seed_hi, k};
+    const TopCellLog top{&s_top->count, s_top->list, reinterpret_cast<float*>(out4 + i)};
 #else
     const NoTopCell top;                                               // diagnostic build (uniforms v2: the cell's midpoint)
 #endif
@@ -209,6 +214,7 @@ embed_kernel(const EmbedArgs a) {
   __shared__ __align__(16) uint32_t s_ks[kTileWords];
   __shared__ __align__(16) float4 s_sign[512];
   __shared__ __align__(16) float4 s_sign16[16];                       // nibble -> +-1.0f x4 (shared-key whole-tile path)
+  __shared__ __align__(16) TopCellShared s_top;                       // outermost-cell elements seen by this CTA (refined in the epilogue)
   const uint32_t tile = kPerLatent ? blockIdx.y : blockIdx.y >> 1;
   const uint32_t tiles = a.tiles_per_latent;
   const uint32_t words = tile_words(a.n_elems, tile);
@@ -216,6 +222,7 @@ embed_kernel(const EmbedArgs a) {
   trace_mark(0);
   griddep_launch_dependents();
   build_sign_lut(s_sign);
+  if (threadIdx.x == 0) s_top.count = 0;
   if (threadIdx.x < 16) {
     const uint32_t n = threadIdx.x;
     s_sign16[n] = make_float4((n & 8u) ? 1.f : -1.f, (n & 4u) ? 1.f : -1.f, (n & 2u) ? 1.f : -1.f, (n & 1u) ? 1.f : -1.f);
@@ -264,13 +271,13 @@ embed_kernel(const EmbedArgs a) {
         pack[j >> 2] |= (nib << 4) << (8u * (j & 3u));
       }
       for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
-        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0, n_f4, pack[0]);
-        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0 + 1, n_f4, pack[1]);
+        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0, n_f4, &s_top, pack[0]);
+        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0 + 1, n_f4, &s_top, pack[1]);
       }
     } else {
       for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
-        embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4);
-        if ((s0 + 1) * 4 * kThreads < n_f4) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4);
+        embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4, &s_top);
+        if ((s0 + 1) * 4 * kThreads < n_f4) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4, &s_top);
       }
     }
     trace_mark(3);
@@ -281,12 +288,27 @@ embed_kernel(const EmbedArgs a) {
                             a.msg_words, a.tiled_words);
       if (n_f4 == kTileF4) {
 #pragma unroll 2
-        for (uint32_t sidx = 0; sidx < 4; ++sidx) embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4);
+        for (uint32_t sidx = 0; sidx < 4; ++sidx) embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4, &s_top);
       } else {
-        for (uint32_t sidx = 0; sidx * 4 * kThreads < n_f4; ++sidx) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4);
+        for (uint32_t sidx = 0; sidx * 4 * kThreads < n_f4; ++sidx) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4, &s_top);
       }
     }
   }
+#if GSWM_TOPCELL
+  // Epilogue (uniforms v3): refine the outermost-cell elements this CTA logged -- one in 8.4 M, so almost always none.
+  __syncthreads();                                                    // all stores and log entries of the CTA are done and visible to it
+  const uint32_t logged = s_top.count < kTopCellSlots ? s_top.count : kTopCellSlots;
+  for (uint32_t e = threadIdx.x; e < logged; e += kThreads) {
+    float* where = s_top.list[e];
+    const uint64_t idx = (uint64_t)(where - a.out);                   // element index within this launch's output
+    const uint64_t lat = idx / (uint64_t)a.n_elems;
+    const uint32_t el = (uint32_t)(idx - lat * (uint64_t)a.n_elems);  // ... within its latent
+    const uint32_t t = el / kTileElems, f4 = (el % kTileElems) >> 2;  // tile; float4 (4 sidx + k) * 256 + tid within the tile
+    const uint32_t sk = f4 / kThreads;
+    const uint64_t g = (((uint64_t)a.first_latent + lat) * tiles + t) * tile_stride + (uint64_t)(sk >> 2) * kThreads + f4 % kThreads;
+    top_cell_fixup(where, g, 4u * (sk & 3u) + (el & 3u), a.off_lo, a.off_hi, a.seed_lo, a.seed_hi);
+  }
+#endif
 }
 
 // Injected-uniform embed (fp64 arithmetic, parity / seeded drop-in mode; not the throughput path).

@@ -122,8 +122,9 @@ __device__ __forceinline__ uint4 philox4x32_keys(uint4 c, const PhiloxKeys& rk) 
 // instead of being represented by its midpoint: a fourth Philox call (counter word 3 = call index 3, key word 1 + k
 // for float4 k) yields a 28-bit m2 and v = 1 - (m2 + 1/2) 2^-51, so that the watermarked noise has the reference's
 // support -- |z| up to 8.2095 = norm.ppf(1 - 2^-53), the largest value gs_insert.py:62-64 can produce for bucket
-// bit 1 -- where the plain 23-bit grid stops at 5.42 (tail mass 6e-8 cut off).  The refinement lives in the rare tail
-// block and is evaluated in float64 (top_cell_quantile below); the hot path is unchanged.
+// bit 1 -- where the plain 23-bit grid stops at 5.42 (tail mass 6e-8 cut off).  The hot loop does not know about it: the
+// rare tail block LOGS such an element in shared memory and the CTA refines its logged elements once, after its last
+// latent (TopCellLog below, embed_kernel's epilogue).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t r;
@@ -238,24 +239,41 @@ __device__ __forceinline__ float top_cell_quantile(uint32_t w) {
   for (int i = 1; i < (int)(sizeof(c) / sizeof(float)); ++i) p = fmaf(p, s, c[i]);
   return p;
 }
-struct NoTopCell {                                                   // test hook / callers without a counter: the cell's midpoint
-  __device__ __forceinline__ float operator()(uint32_t, float x) const { return quantile_tail(x); }
+struct NoTopCell {                                                   // test hook / callers without a counter: the cell keeps its midpoint
+  static constexpr bool kLogs = false;
+  __device__ __forceinline__ void operator()(uint32_t) const {}
 };
-// Element j of float4 k of the super-iteration whose Philox counter is g_base + g_add (words 0..1), (off_lo, off_hi)
-// (words 2..3 of call 0): the refinement bits are word j of Philox call 3 of that counter under key (seed_lo, seed_hi + k).
-struct TopCellRefine {
-  uint64_t g_base;          // loop-carried counter of the caller (live across the loop whatever happens here)
-  uint32_t g_add;
-  uint32_t off_lo, off_hi, seed_lo, seed_hi, k;
-  __device__ __forceinline__ float operator()(uint32_t j, float) const {
-    uint64_t gb = g_base;
-    asm volatile("" : "+l"(gb));      // opaque copy: the counter is re-derived HERE, in the rare block, instead of being kept
-                                      // alive (two registers) across the whole super-iteration for it
-    const uint64_t g = gb + g_add;
-    const uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), off_lo, off_hi + 3u), seed_lo, seed_hi + k);
-    return top_cell_quantile(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
+// How the outermost cell gets refined without costing the hot loop anything.  Tried first, and measured (4096 SD-2.1
+// latents, profiles/r02b_kbench.jsonl): the refinement inline in the patch block -- 69.6 us against 55.0 us, the loop body
+// (2561 instructions, every patch block dragging a Philox call behind it) no longer fits the instruction cache, and what
+// the hot path jumps over is fetched all the same; the rare formulas as out-of-line calls -- 58.2 .. 59.4 us, a call in
+// the loop makes the compiler re-materialise its constants after every patch block; a per-thread mask tested after each
+// super-iteration -- 58.5 us.  What costs nothing: the patch block appends the ADDRESS of such an element to a small
+// list in SHARED memory (one atomic and one store inside an already rare block) and the CTA walks the list once, after
+// its last latent.  A CTA sees one such element per 8.4 M it produces; the list holds 64 (an overflowing
+// element would keep the cell's midpoint -- still a sample of the right bucket).
+constexpr uint32_t kTopCellSlots = 64;
+struct TopCellLog {
+  static constexpr bool kLogs = true;
+  uint32_t* count;          // shared memory
+  float** list;             // shared memory, kTopCellSlots entries: the ADDRESS of the element says everything (which latent,
+                            // tile, super-iteration, lane, position -- hence which Philox counter), so that is all that is logged
+  float* out_f4;            // address of the float4 being produced
+  __device__ __forceinline__ void operator()(uint32_t j) const {
+    const uint32_t slot = atomicAdd(count, 1u);
+    if (slot < kTopCellSlots) list[slot] = out_f4 + j;
   }
 };
+// The epilogue's half.  `idx`: the element's index in the launch's output, `g`: Philox counter words 0..1 of its
+// super-iteration, kj = 4 k + j (element j of float4 k): word j of Philox call 3 of that counter under key
+// (seed_lo, seed_hi + k) -> |z|; the sign is the one the element was stored with.
+__device__ __forceinline__ void top_cell_fixup(float* where, uint64_t g, uint32_t kj, uint32_t off_lo, uint32_t off_hi,
+                                               uint32_t seed_lo, uint32_t seed_hi) {
+  const uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), off_lo, off_hi + 3u), seed_lo, seed_hi + (kj >> 2));
+  const uint32_t j = kj & 3u;
+  const float mag = top_cell_quantile(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
+  *where = copysignf(mag, *where);
+}
 constexpr float kTopCellX = -18.5f;
 
 #ifndef GSWM_TAIL_INT
@@ -301,13 +319,17 @@ __device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1,
   bool any_tail = fminf(fminf(x01.x, x01.y), fminf(x23.x, x23.y)) < GSWM_HNQ_XSPLIT;
   if (kWarpUniformTail) any_tail = __any_sync(0xFFFFFFFFu, any_tail);
 #endif
-  if (any_tail) {
+  if (__builtin_expect(any_tail, 0)) {
     // per element the decision is its own x (the f bit patterns are dead by now: nothing is kept alive across the Horner
     // chains for this block); the outermost cell is x < -18.5 (m = 2^23 - 1: x = -19.0; m = 2^23 - 2: x = -17.4)
-    if (x01.x < GSWM_HNQ_XSPLIT) g01.x = x01.x < kTopCellX ? top(0, x01.x) : quantile_tail(x01.x);
-    if (x01.y < GSWM_HNQ_XSPLIT) g01.y = x01.y < kTopCellX ? top(1, x01.y) : quantile_tail(x01.y);
-    if (x23.x < GSWM_HNQ_XSPLIT) g23.x = x23.x < kTopCellX ? top(2, x23.x) : quantile_tail(x23.x);
-    if (x23.y < GSWM_HNQ_XSPLIT) g23.y = x23.y < kTopCellX ? top(3, x23.y) : quantile_tail(x23.y);
+    auto patch = [&](uint32_t j, float x) {
+      if (TopCell::kLogs && x < kTopCellX) top(j);                    // outermost cell: noted for the epilogue, midpoint for now
+      return quantile_tail(x);
+    };
+    if (x01.x < GSWM_HNQ_XSPLIT) g01.x = patch(0, x01.x);
+    if (x01.y < GSWM_HNQ_XSPLIT) g01.y = patch(1, x01.y);
+    if (x23.x < GSWM_HNQ_XSPLIT) g23.x = patch(2, x23.x);
+    if (x23.y < GSWM_HNQ_XSPLIT) g23.y = patch(3, x23.y);
   }
 #endif
 #ifdef GSWM_WHATIF_NOSIGN

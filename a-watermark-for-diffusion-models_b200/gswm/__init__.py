@@ -9,7 +9,7 @@ Host side of libgswm.so (include/gswm.h).  Mirrors of the reference's call sites
 There is no CPU fallback: importing works without a GPU (so the C-ABI export check can run), but
 every compute call needs a CUDA device and the built library.
 """
-from . import _lib
+from . import _lib, sharding
 from ._lib import GswmError, build, launch_count
 from .codec import (DEFAULT_KEY_HEX, DEFAULT_NONCE_HEX, Comm, ExtractResult, HostPipe, KeyMaterial, chacha20_keystream,
                     choose_watermark_length, embed_batch, embed_batch_injected, embed_batch_mt19937, embed_extract_batch,
@@ -18,4 +18,4 @@ from .codec import (DEFAULT_KEY_HEX, DEFAULT_NONCE_HEX, Comm, ExtractResult, Hos
 __all__ = ["GswmError", "build", "launch_count", "DEFAULT_KEY_HEX", "DEFAULT_NONCE_HEX", "Comm", "ExtractResult", "HostPipe",
            "KeyMaterial", "chacha20_keystream", "choose_watermark_length", "embed_batch", "embed_batch_injected",
            "embed_batch_mt19937", "embed_extract_batch", "extract_batch", "mt19937_uniform", "pad_message",
-           "resolve_key_nonce", "_lib"]
+           "resolve_key_nonce", "sharding", "_lib"]

@@ -16,7 +16,7 @@ _CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 _INCLUDE = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include")
 # GSWM_LIB: load another build of the same ABI instead (A/B runs of kernel variants through bench.py / the tests)
 LIB_PATH = os.environ.get("GSWM_LIB") or os.path.join(_HERE, "libgswm.so")
-SOURCES = ["gswm_kernels.cu", "gswm_mt19937.cu", "gswm_comm.cu", "gswm_pipe.cu"]
+SOURCES = ["gswm_kernels.cu", "gswm_mt19937.cu", "gswm_comm.cu", "gswm_pipe.cu", "gswm_microbench.cu"]
 
 ABI_VERSION = 2
 GSWM_F32, GSWM_F16, GSWM_BF16, GSWM_F64 = 0, 1, 2, 3
@@ -24,6 +24,7 @@ CTR_MATCHED_BITS, CTR_TOTAL_BITS, CTR_EXACT_MSGS, CTR_TOTAL_MSGS, CTR_NAN_LATENT
 FLAG_NAN, FLAG_RANGE = 1, 2
 JOB_PER_LATENT, JOB_KEYS_IN_FLIGHT = 1, 2
 E_COMM = -6
+ISSUE_KINDS = {"FFMA2": 0, "IMAD.WIDE": 1, "LOP3": 2, "MUFU.LG2": 3, "FFMA(imm)": 4, "IMAD.WIDE+LOP3": 5}
 COMM_HANDLE_BYTES, COMM_MAX_VALUES, COMM_MAX_RANKS = 64, 8, 32
 
 EXPORTS = [
@@ -32,7 +33,7 @@ EXPORTS = [
     "gswm_comm_connect", "gswm_comm_connect_local", "gswm_comm_destroy", "gswm_comm_status",
     "gswm_comm_allreduce_counters", "gswm_allreduce_counters", "gswm_pipe_create", "gswm_pipe_destroy",
     "gswm_pipe_embed", "gswm_pipe_embed_injected", "gswm_pipe_extract", "gswm_launch_count",
-    "gswm_debug_bucket_quantile", "gswm_debug_norm_ppf", "gswm_debug_top_cell", "gswm_debug_philox4x32", "gswm_philox_rounds",
+    "gswm_debug_bucket_quantile", "gswm_debug_norm_ppf", "gswm_debug_top_cell", "gswm_debug_philox4x32", "gswm_debug_issue_rate", "gswm_philox_rounds",
 ]
 
 
@@ -63,10 +64,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps.append(os.path.join(_INCLUDE, "gswm.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    cmd = nvcc_command(extra=("-Xptxas", "-v") if verbose else ())
+    tmp = LIB_PATH + ".building"                # link into a scratch name, then rename: a reader never sees half a library
+    cmd = nvcc_command(out=tmp, extra=("-Xptxas", "-v") if verbose else ())
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(res.stderr)
     return LIB_PATH
@@ -120,6 +123,8 @@ def lib() -> C.CDLL:
         L.gswm_debug_norm_ppf.argtypes = [vp, i64, vp, vp]
         L.gswm_debug_philox4x32.argtypes = [vp, i64, i32, vp, vp]
         L.gswm_debug_top_cell.argtypes = [vp, i64, vp, vp]
+        L.gswm_debug_issue_rate.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.gswm_debug_issue_rate.restype = C.c_int
         for name in ("gswm_chacha20_keystream", "gswm_embed", "gswm_embed_injected", "gswm_embed_mt19937",
                      "gswm_mt19937_uniform", "gswm_extract", "gswm_extract_allreduce", "gswm_comm_create",
                      "gswm_comm_connect", "gswm_comm_connect_local", "gswm_comm_status", "gswm_comm_allreduce_counters",

@@ -48,6 +48,13 @@ def parse():
     ap.add_argument("--shape", default="sd21", choices=sorted(SHAPES))
     ap.add_argument("--msg-bits", type=int, default=256)
     ap.add_argument("--per-latent-keys", action="store_true", help="BASELINE config[4]: distinct key/nonce/message per latent")
+    ap.add_argument("--total-latents", type=int, default=None,
+                    help="strong scaling: this many latents in total, sharded over the ranks (BASELINE configs[3]: --shape sdxl "
+                         "--total-latents 65536; configs[4]: --per-latent-keys --total-latents 1048576)")
+    ap.add_argument("--chunk-latents", type=int, default=None, help="latents per kernel launch when a shard is processed in chunks")
+    ap.add_argument("--sustain-seconds", type=float, default=1.2, help="length of the sustained leg (0 = skip)")
+    ap.add_argument("--no-issue-rates", action="store_true")
+    ap.add_argument("--collective", default="auto", choices=["auto", "gswm", "nccl"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
@@ -58,6 +65,10 @@ def parse():
 def workload_name(args):
     c, h, w = SHAPES[args.shape]
     keys = "per-latent key/nonce/message" if args.per_latent_keys else "shared default key/nonce, message 'lthero'"
+    if getattr(args, "total_latents", None):
+        which = "configs[4]" if args.per_latent_keys else "configs[3]"
+        return (f"BASELINE {which}: {args.total_latents} latents ({c}x{h}x{w}) in total, sharded over the GPUs, embed + extract "
+                f"round trip (per-sample noise, every message must decode exactly), {args.msg_bits}-bit message, {keys}")
     return (f"BASELINE configs[1]+[2]: embed {args.batch} latents ({c}x{h}x{w}, per-sample noise) + extract {args.batch} "
             f"noisy latents (sigma={SIGMA}), {args.msg_bits}-bit message, {keys}")
 
@@ -213,6 +224,11 @@ class ClockSampler:
                 os.unlink(self.path)
             except OSError:
                 pass
+        self.rows = rows
+        return self.window_stats(window)
+
+    def window_stats(self, window):
+        rows = getattr(self, "rows", None) or []
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         inside = [r for r in rows if window and window[0] <= r[0] <= window[1]]
@@ -276,11 +292,56 @@ def ncu_pipe_summary(kernel):
         return None
 
 
+def gpu_local_cpus_nvml(index):
+    """CPU affinity of GPU `index` as NVML reports it (the ideal CPUs for its PCIe root), intersected with this process's
+    affinity; empty set if unknown.  /sys's numa_node reads -1 inside these containers, NVML still knows."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        return cpus & os.sched_getaffinity(0)
+    except Exception:  # noqa: BLE001
+        return set()
+
+
+def verbatim_reference_note():
+    """BASELINE config[0] timed on the unmodified reference in the build container (tools/verbatim_reference_timing.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_verbatim_reference.json")) as f:
+            v = json.load(f)
+        return ("the UNMODIFIED reference (gs_insert.py:8-75 + extract.py:72-110), 1 core, build container, median of %d: %.2f s embed + "
+                "%.2f s extract per latent = %.3f pairs/s (profiles/r02_verbatim_reference.json)"
+                % (v["repeats"], v["embed_s_median"], v["extract_s_median"], v["pairs_per_s"]))
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def embed_issue_profile():
+    """Executed warp instructions per latent element of the embed kernel, from the committed ncu capture of this build
+    (smsp__inst_executed.sum / elements): a property of the binary, not of the run."""
+    for name in ("r02_embed_ncu_summary.json", "r01h_embed_ncu_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                k = json.load(f)["kernels"][0]
+            inst = float(k["smsp__inst_executed.sum"]["value"])
+            return inst / (4096 * 16384), f"profiles/{name}"
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
+
+
 def run_gpu_arm(args):
     # stdout carries the one JSON line only: libraries that printf to fd 1 (NCCL's version banner) go to stderr
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
+    import ctypes as C
+    import datetime as _dt
+    import threading
+
     import torch
     import torch.distributed as dist
 
@@ -299,80 +360,146 @@ def run_gpu_arm(args):
         gswm.build()                                  # no-op when libgswm.so is up to date; there is no fallback path
     if world > 1:
         dist.barrier()
-    gswm._lib.lib()
+    lib = gswm._lib.lib()
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
         sampler.start()                               # started early: it needs a few hundred ms before its first line
 
+    from gswm.codec import _DeviceJob
     shape = SHAPES[args.shape]
     n = int(np.prod(shape))
-    B, L = args.batch, args.msg_bits
-    first = rank * B                                   # global latent index of this rank's shard
+    L = args.msg_bits
+    strong = args.total_latents is not None
+    if strong:                                         # BASELINE configs[3] / [4]: a fixed total, sharded over the ranks
+        lo, hi = gswm.sharding.shard_range(args.total_latents, rank, world)
+        B, first = hi - lo, lo
+    else:                                              # weak scaling: every rank its own B latents
+        B, first = args.batch, rank * args.batch
+    chunk = min(B, args.chunk_latents or max(1, (8 << 30) // (n * 4)))     # latents per launch (<= 8 GiB of fp32 per buffer)
+    pipeline = strong or chunk < B
+    n_chunks = (B + chunk - 1) // chunk
     if args.per_latent_keys:
-        rs = np.random.RandomState(2025)
-        allk = rs.bytes(32 * B * world); alln = rs.bytes(16 * B * world); allm = rs.bytes((L // 8) * B * world)
-        km = gswm.KeyMaterial.make(allk[32 * first:32 * (first + B)], alln[16 * first:16 * (first + B)],
-                                   allm[(L // 8) * first:(L // 8) * (first + B)], L)
+        rs = np.random.RandomState(2025)               # keys / nonces / messages from RandomState(2025).bytes
+        tot = args.total_latents if strong else B * world
+        allk = np.frombuffer(rs.bytes(32 * tot), np.uint8).reshape(tot, 32)
+        alln = np.frombuffer(rs.bytes(16 * tot), np.uint8).reshape(tot, 16)
+        allm = np.frombuffer(rs.bytes((L // 8) * tot), np.uint8).reshape(tot, L // 8)
+        km = gswm.KeyMaterial.make(allk[first:first + B], alln[first:first + B], allm[first:first + B], L)
     else:
         km = gswm.KeyMaterial.make(bytes.fromhex(gswm.DEFAULT_KEY_HEX), bytes.fromhex(gswm.DEFAULT_NONCE_HEX),
                                    gswm.pad_message("lthero", L // 8), L)
     seed = 0x5EED
+    NC = gswm._lib.N_COUNTERS
 
-    # ---- resident inputs: key material on device, noisy latents for the extract side -------------------------
-    from gswm.codec import _DeviceJob
-    from gswm.sharding import allreduce_counters
-    import ctypes as C
-    lib = gswm._lib.lib()
-    dj = _DeviceJob(km, B, n, dev)
-    z = torch.empty((B, *shape), dtype=torch.float32, device=dev)
+    # ---- resident buffers -------------------------------------------------------------------------------------------
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
-    gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
-    g = torch.Generator(dev).manual_seed(99 + rank)
-    z_noisy = z + SIGMA * torch.randn(z.shape, device=dev, generator=g)
-    msgs = torch.empty((B, L // 8), dtype=torch.uint8, device=dev)
-    matched = torch.empty((B,), dtype=torch.int32, device=dev)
-    counters = torch.zeros((gswm._lib.N_COUNTERS,), dtype=torch.int64, device=dev)
-
-    # The two halves of a step are independent (embed writes z, extract reads z_noisy), one is bound by the FMA pipes
-    # and the other by HBM, so they are launched on two streams and share the SMs: the step then runs at the pair's
-    # HBM roofline instead of the sum of two kernels each leaving one resource idle (tools/cobench.py).
     xstream = torch.cuda.Stream(dev)
     xp = xstream.cuda_stream
+    dj_all = _DeviceJob(km, B, n, dev)                  # key material on the device (all of this rank's rows)
+    row_k, row_n, row_m = (32, 16, L // 8) if km.per_latent else (0, 0, 0)
 
-    def step(serial=False):
-        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
-        gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
-                                         None, counters.data_ptr(), sp if serial else xp), "gswm_extract")
+    def chunk_job(c):
+        """ctypes job for chunk c of this rank's shard (per-latent rows are offset into the resident key arrays)."""
+        f0 = c * chunk
+        nb = min(chunk, B - f0)
+        j = dj_all.job
+        return gswm._lib.Job(nb, n, L, j.flags, j.keys + f0 * row_k, j.nonces + f0 * row_n, j.msgs + f0 * row_m), f0, nb
+
+    jobs = [chunk_job(c) for c in range(n_chunks)]
+    msgs = torch.empty((chunk, L // 8), dtype=torch.uint8, device=dev)
+    matched = torch.empty((chunk,), dtype=torch.int32, device=dev)
+    counters = torch.zeros((NC,), dtype=torch.int64, device=dev)
+    reduced = torch.zeros((NC,), dtype=torch.int64, device=dev)
+    zbuf = [torch.empty((chunk, *shape), dtype=torch.float32, device=dev) for _ in range(2 if pipeline else 1)]
+    z = zbuf[0]
+    if not pipeline:
+        # BASELINE configs[1]+[2]: the extract side reads its own resident batch of noisy latents (sigma = 0.325)
+        gswm._lib.check(lib.gswm_embed(C.byref(jobs[0][0]), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
+        g = torch.Generator(dev).manual_seed(99 + rank)
+        z_noisy = z + SIGMA * torch.randn(z.shape, device=dev, generator=g)
+    else:
+        z_noisy = None
+
+    # ---- the path's one collective: the sum of the bit-match counters over the ranks ------------------------------------
+    comm, collective = None, "none (1 GPU)"
+    if world > 1:
+        collective = "NCCL all-reduce through torch.distributed (c10d)"
+        if args.collective != "nccl":
+            try:
+                comm = gswm.Comm(dev)
+                collective = ("gswm_comm: fused into the last extract launch of the timed region (gswm_extract_allreduce) -- "
+                              "per-rank mailboxes in HBM, peers store into them over NVLink (CUDA IPC mapping), no host round trip")
+            except Exception as e:  # noqa: BLE001
+                if args.collective == "gswm":
+                    raise
+                collective += f" [gswm_comm unavailable: {e}]"
+
+    def launch_embed(c, buf, st):
+        job, f0, _ = jobs[c]
+        gswm._lib.check(lib.gswm_embed(C.byref(job), seed, 0, first + f0, buf.data_ptr(), st), "gswm_embed")
+
+    def launch_extract(c, src, st, fused=False):
+        job = jobs[c][0]
+        if fused:
+            gswm._lib.check(lib.gswm_extract_allreduce(C.byref(job), src.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
+                                                       None, counters.data_ptr(), comm.handle, reduced.data_ptr(), st),
+                            "gswm_extract_allreduce")
+        else:
+            gswm._lib.check(lib.gswm_extract(C.byref(job), src.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(), None,
+                                             counters.data_ptr(), st), "gswm_extract")
+
+    # The two halves of a step are bound by different resources (embed: the SMs' FMA pipes, extract: HBM), so they are
+    # launched on two streams and share the SMs.  Default workload: they are independent (embed writes z, extract reads
+    # z_noisy).  Sharded-total workloads (configs[3], [4]): a ROUND TRIP in chunks -- extract decodes the chunk embed just
+    # wrote (two buffers: embed of chunk k+1 overlaps extract of chunk k), so every message must come back exactly.
+    ev_e = [torch.cuda.Event() for _ in range(2)]
+    ev_x = [torch.cuda.Event() for _ in range(2)]
+
+    def step(serial=False, last=False):
+        if not pipeline:
+            launch_embed(0, z, sp)
+            launch_extract(0, z_noisy, sp if serial else xp, fused=last and comm is not None)
+            return
+        for c in range(n_chunks):
+            b_ = c & 1
+            if c >= 2 and not serial:
+                stream.wait_event(ev_x[b_])                    # the buffer's previous reader is done
+            launch_embed(c, zbuf[b_], sp)
+            if serial:
+                launch_extract(c, zbuf[b_], sp, fused=last and c == n_chunks - 1 and comm is not None)
+            else:
+                ev_e[b_].record(stream)
+                xstream.wait_event(ev_e[b_])
+                launch_extract(c, zbuf[b_], xp, fused=last and c == n_chunks - 1 and comm is not None)
+                ev_x[b_].record(xstream)
 
     def timed(n_steps, serial=False, reduce=True):
         """Device time of n_steps steps: fork the extract stream off the launch stream, join it back before the end event.
-        The path's only collective -- the FINAL all-reduce of the 4 int64 bit-match counters the extract kernels have been
-        accumulating (north_star) -- runs once, after the last step and inside the timed region."""
+        The path's only collective -- the FINAL sum of the bit-match counters the extract kernels have been accumulating
+        (north_star) -- is part of the timed region: fused into the last extract launch (gswm_comm), or one c10d all-reduce."""
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         joined = torch.cuda.Event()
         t0.record(stream)
         xstream.wait_event(t0)
-        for _ in range(n_steps):
-            step(serial)
+        for i in range(n_steps):
+            step(serial, last=reduce and world > 1 and i == n_steps - 1)
         joined.record(xstream)
         stream.wait_event(joined)
-        if world > 1 and reduce:
+        if world > 1 and reduce and comm is None:
             reduced.copy_(counters)
-            allreduce_counters(reduced)                # gswm/sharding.py: dist.all_reduce(SUM) over NCCL
+            dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
         t1.record(stream)
         return t0, t1
-
-    reduced = torch.zeros_like(counters)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    timed(max(3, args.warmup))                         # warm-up steps (and NCCL's lazy communicator set-up)
+    warm = max(3, args.warmup)
+    timed(warm)                                        # warm-up steps (and the communicator's first exchange)
     barrier()
-    import datetime as _dt
     if rank == 0:
         sampler.wait_ready()
     launches0 = gswm.launch_count()
@@ -382,21 +509,23 @@ def run_gpu_arm(args):
     barrier()
     launches = gswm.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
-    n_steps_total = max(3, args.warmup) + args.steps
+    n_steps_total = warm + args.steps
     torch.cuda.synchronize(dev)
     final = (reduced if world > 1 else counters).cpu().numpy().tolist()   # accumulated over every step so far
-    # every message of every step decodes exactly at sigma = 0.325
-    exact = final[2] == final[3] == B * world * n_steps_total and final[0] == final[1] == B * world * L * n_steps_total
+    tot_lat = (args.total_latents if strong else B * world) * n_steps_total
+    # every message of every step decodes exactly (sigma = 0.325 / noise-free round trip), nothing was rejected
+    exact = final[2] == final[3] == tot_lat and final[0] == final[1] == tot_lat * L and final[4] == final[5] == 0
+    if comm is not None and comm.status() != 0:
+        exact = False
+
     # Per-kernel durations for the roofline block: the same launches, each kernel back to back `inst_steps` times
     # between one pair of events (so no event record or dependent-launch gap sits inside the measured interval).
-    inst_steps = min(args.steps, 200)
-    # the same step with both kernels on ONE stream (no co-scheduling), for reference
+    inst_steps = max(1, min(args.steps, 200) // n_chunks) if pipeline else min(args.steps, 200)
     barrier()
-    s_begin, s_end = timed(inst_steps, serial=True, reduce=False)
+    s_begin, s_end = timed(max(1, min(args.steps, 200 // n_chunks if pipeline else 200)), serial=True, reduce=False)
     barrier()
-    serial_ms = s_begin.elapsed_time(s_end) / inst_steps
-    # three bursts per kernel, each between one event pair; `ms` is the best burst (min and median), the
-    # median is reported next to it
+    serial_ms = s_begin.elapsed_time(s_end) / max(1, min(args.steps, 200 // n_chunks if pipeline else 200))
+
     def burst(launch):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -407,45 +536,83 @@ def run_gpu_arm(args):
         barrier()
         return e0.elapsed_time(e1) / inst_steps
 
-    def launch_embed():
-        gswm._lib.check(lib.gswm_embed(C.byref(dj.job), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
-
-    def launch_extract():
-        gswm._lib.check(lib.gswm_extract(C.byref(dj.job), z_noisy.data_ptr(), 0, msgs.data_ptr(), None, matched.data_ptr(),
-                                         None, counters.data_ptr(), sp), "gswm_extract")
-
-    embed_bursts = sorted(burst(launch_embed) for _ in range(3))
-    extract_bursts = sorted(burst(launch_extract) for _ in range(3))
+    src = z_noisy if not pipeline else zbuf[0]
+    if pipeline:
+        launch_embed(0, zbuf[0], sp)
+    embed_bursts = sorted(burst(lambda: launch_embed(0, zbuf[0], sp)) for _ in range(3))
+    extract_bursts = sorted(burst(lambda: launch_extract(0, src, sp)) for _ in range(3))
     embed_ms, extract_ms = embed_bursts[0], extract_bursts[0]
     embed_med, extract_med = embed_bursts[1], extract_bursts[1]
-    clocks = sampler.stop((load_begin, _dt.datetime.now())) if rank == 0 else None
-    tm = torch.tensor([total_ms, embed_ms, extract_ms, serial_ms], dtype=torch.float64, device=dev)
+    burst_latents = jobs[0][2]
+    kernels_end = _dt.datetime.now()
+
+    # ---- sustained leg: >= --sustain-seconds of back-to-back steps, whatever --steps was --------------------------------
+    sustained = None
+    if args.sustain_seconds > 0:
+        per_step = total_ms / args.steps
+        n_sus = int(min(200000, max(args.steps, args.sustain_seconds * 1e3 / max(per_step, 1e-3))))
+        barrier()
+        sus_begin = _dt.datetime.now()
+        s0, s1 = timed(n_sus, reduce=False)
+        barrier()
+        sus_end = _dt.datetime.now()
+        sus_ms = s0.elapsed_time(s1) / n_sus
+        sustained = {"steps": n_sus, "ms_per_step": sus_ms, "window": (sus_begin, sus_end)}
+
+    # ---- issue-rate denominators, same run, same GPU ---------------------------------------------------------
+    issue = None
+    if rank == 0 and not args.no_issue_rates:
+        issue = {}
+        for name, kind in gswm._lib.ISSUE_KINDS.items():
+            r_, g_ = C.c_double(), C.c_double()
+            if lib.gswm_debug_issue_rate(kind, C.byref(r_), C.byref(g_)) == 0:
+                issue[name] = {"warp_inst_per_clk_per_smsp": round(r_.value, 4), "sm_ghz": round(g_.value, 3)}
+    barrier()
+    clocks = sampler.stop((load_begin, kernels_end)) if rank == 0 else None     # timed region + per-kernel bursts; the sustained leg has its own window
+    if rank == 0 and sustained is not None:
+        sc = sampler.window_stats(sustained.pop("window"))
+        sustained.update({"sm_mhz": sc.get("sm_mhz"), "reasons": sc.get("reasons"), "power_w_max": sc.get("power_w_max"),
+                          "clock_samples": sc.get("samples")})
+    elif sustained is not None:
+        sustained.pop("window")
+    tm = torch.tensor([total_ms, embed_ms, extract_ms, serial_ms, sustained["ms_per_step"] if sustained else 0.0],
+                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms, embed_ms, extract_ms, serial_ms = tm.cpu().tolist()
+    total_ms, embed_ms, extract_ms, serial_ms, sus_ms = tm.cpu().tolist()
     ms_per_step = total_ms / args.steps
-    value = B * world / (ms_per_step * 1e-3)
+    lat_per_step = args.total_latents if strong else B * world
+    value = lat_per_step / (ms_per_step * 1e-3)
+    if sustained is not None:
+        sustained["ms_per_step"] = sus_ms
+        sustained["value"] = lat_per_step / (sus_ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI pipe (PCIe inside the timed region) -------------------------------
     # Two pipes (one per direction) driven from two host threads: the embed side's D2H and the extract side's H2D
     # use the two directions of the PCIe link at the same time (ctypes releases the GIL during the calls).
-    import threading
     # host buffers and the pipe's staging live on the GPU's own NUMA node (first touch happens under this affinity)
     affinity0 = os.sched_getaffinity(0)
-    local_cpus = gpu_local_cpus(torch, local)
+    local_cpus = gpu_local_cpus(torch, local) or gpu_local_cpus_nvml(local)
     if local_cpus:
         os.sched_setaffinity(0, local_cpus)
-    pipe_e = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, B))
-    pipe_x = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, B))
-    h_out = torch.empty((B, *shape), dtype=torch.float32).pin_memory()
-    h_in = z_noisy.cpu().pin_memory()
+    Be = min(B, max(1, (1 << 30) // (n * 4)))          # e2e batch: the rank's shard, bounded to 1 GiB per direction
+    kme = km if not km.per_latent else gswm.KeyMaterial.make(km.keys[:Be], km.nonces[:Be], km.msgs[:Be], L)
+    pipe_e = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, Be))
+    pipe_x = gswm.HostPipe(local, max_elems=n, chunk_latents=min(E2E_CHUNK, Be))
+    h_out = torch.empty((Be, *shape), dtype=torch.float32).pin_memory()
+    if pipeline:
+        launch_embed(0, zbuf[0], sp)
+        torch.cuda.synchronize(dev)
+        h_in = zbuf[0][:Be].cpu().pin_memory()
+    else:
+        h_in = z_noisy[:Be].cpu().pin_memory()
     e2e_steps = max(1, args.e2e_steps)
     box = {}
 
     def e2e_step():
-        t = threading.Thread(target=lambda: pipe_e.embed(h_out, km, seed, 0, first))
+        t = threading.Thread(target=lambda: pipe_e.embed(h_out, kme, seed, 0, first))
         t.start()
-        box["x"] = pipe_x.extract(h_in, km)
+        box["x"] = pipe_x.extract(h_in, kme)
         t.join()
         return box["x"]
 
@@ -453,19 +620,44 @@ def run_gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        _, _, _, h_cnt, _ = e2e_step()
+        _, _, _, h_cnt, h_flags = e2e_step()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    barrier()
+    # the box's ceiling for exactly this traffic: plain pinned cudaMemcpyAsync of the same bytes, both directions at once,
+    # every rank at the same time -- no kernels, no pipe
+    d_a = torch.empty((Be, n), dtype=torch.float32, device=dev)
+    d_b = torch.empty((Be, n), dtype=torch.float32, device=dev)
+    cs1, cs2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_both():
+        with torch.cuda.stream(cs1):
+            d_a.copy_(h_in.reshape(Be, n), non_blocking=True)
+        with torch.cuda.stream(cs2):
+            h_out.reshape(Be, n).copy_(d_b, non_blocking=True)
+
+    copy_both()
+    barrier()
+    tc = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_both()
+    torch.cuda.synchronize(dev)
+    ceil_s = time.perf_counter() - tc
+    te = torch.tensor([e2e_s, ceil_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    e2e_value = B * world * e2e_steps / e2e_s
-    e2e_ok = int(h_cnt[2]) == B and int(h_cnt[0]) == B * L
+    e2e_s, ceil_s = te.cpu().tolist()
+    e2e_value = Be * world * e2e_steps / e2e_s
+    e2e_checks = {"all_messages_exact": int(h_cnt[2]) == Be and int(h_cnt[0]) == Be * L, "none_rejected": not bool(h_flags.any())}
+    e2e_ok = all(e2e_checks.values())
     # the embedded latents that came back over PCIe must be the ones the resident path produced
-    e2e_ok = e2e_ok and bool(torch.equal(h_out[:8], z[:8].cpu()))
-    key_bytes = km.keys.nbytes + km.nonces.nbytes + (km.msgs.nbytes if km.msgs is not None else 0)
-    h2d = B * n * 4 + key_bytes * 2                  # latents in + key material once per pipe call
-    d2h = B * n * 4 + B * (L // 8) + B * 4 + 32
+    chk = torch.empty((min(8, Be), *shape), dtype=torch.float32, device=dev)
+    cj = gswm._lib.Job(chk.shape[0], n, L, dj_all.job.flags, dj_all.job.keys, dj_all.job.nonces, dj_all.job.msgs)
+    gswm._lib.check(lib.gswm_embed(C.byref(cj), seed, 0, first, chk.data_ptr(), sp), "gswm_embed")
+    e2e_checks["embedded_latents_equal_resident_path"] = bool(torch.equal(h_out[:chk.shape[0]], chk.cpu()))
+    e2e_ok = e2e_ok and e2e_checks["embedded_latents_equal_resident_path"]
+    key_bytes = kme.keys.nbytes + kme.nonces.nbytes + (kme.msgs.nbytes if kme.msgs is not None else 0)
+    h2d = Be * n * 4 + key_bytes * 2                  # latents in + key material once per pipe call
+    d2h = Be * n * 4 + Be * (L // 8) + Be * 4 + Be + 8 * NC
     pipe_e.close()
     pipe_x.close()
     os.sched_setaffinity(0, affinity0)
@@ -473,22 +665,46 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
     if rank != 0:
+        if comm is not None:
+            comm.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = measured_peak_gbs()
-    lat_bytes = B * n * 4
+    lat_bytes = burst_latents * n * 4                  # algorithmic bytes of ONE launch of either kernel (4 B per element)
+    step_bytes = 2 * B * n * 4                         # ... and of one step on one GPU
     k_embed = {"ms": embed_ms, "ms_median": embed_med, "GBps": lat_bytes / (embed_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
     k_extract = {"ms": extract_ms, "ms_median": extract_med, "GBps": lat_bytes / (extract_ms * 1e-3) / 1e9, "algorithmic_bytes": lat_bytes}
     dom_name, dom = ("embed_kernel", k_embed) if embed_ms >= extract_ms else ("extract_kernel", k_extract)
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["GBps"] / peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
+    # issue view of the embed kernel: executed warp instructions (ncu, per element) x elements / time, against the measured
+    # one-instruction-per-clock peak and against the pipe model (sum over instruction classes of count / measured class rate)
+    ipe, ipe_src = embed_issue_profile()
+    issue_view = None
+    if issue and ipe and "FFMA(imm)" in issue:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        ghz = issue["FFMA(imm)"]["sm_ghz"]
+        peak_wi = issue["FFMA(imm)"]["warp_inst_per_clk_per_smsp"] * 4 * sms * ghz * 1e9      # warp instructions / s, whole GPU
+        ach_wi = ipe * burst_latents * n / (embed_ms * 1e-3)
+        issue_view = {"achieved": ach_wi, "peak": peak_wi, "unit": "warp-inst/s", "frac": ach_wi / peak_wi,
+                      "inst_per_element": round(ipe, 3), "inst_source": ipe_src,
+                      "peak_source": "gswm_debug_issue_rate(FFMA imm) in this run: %.3f warp-inst/clk/SMSP x 4 x %d SMs x %.3f GHz"
+                                     % (issue["FFMA(imm)"]["warp_inst_per_clk_per_smsp"], sms, ghz)}
+    hbm_frac = dom["GBps"] / peak
+    bound = "hbm"
+    if dom_name == "embed_kernel" and issue_view and issue_view["frac"] > hbm_frac:
+        bound = "issue"
+    roofline = {"bound": bound, "kernel": dom_name, "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": hbm_frac, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
+                "issue": issue_view, "issue_rates": issue,
                 "kernels": {"embed_kernel": dict(k_embed, frac=k_embed["GBps"] / peak, ncu=ncu_pipe_summary("embed_kernel")),
                             "extract_kernel": dict(k_extract, frac=k_extract["GBps"] / peak, ncu=ncu_pipe_summary("extract_kernel"))},
                 # the whole co-scheduled step against the same peak: both kernels' algorithmic bytes / step time
-                "step": {"ms": ms_per_step, "GBps": 2 * lat_bytes / (ms_per_step * 1e-3) / 1e9, "algorithmic_bytes": 2 * lat_bytes,
-                         "frac": 2 * lat_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "serial_ms": serial_ms}}
+                "step": {"ms": ms_per_step, "GBps": step_bytes / (ms_per_step * 1e-3) / 1e9, "algorithmic_bytes": step_bytes,
+                         "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "serial_ms": serial_ms}}
+    if sustained is not None:
+        sustained["GBps"] = step_bytes / (sustained["ms_per_step"] * 1e-3) / 1e9
+        sustained["frac"] = sustained["GBps"] / peak
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -498,27 +714,40 @@ def run_gpu_arm(args):
         v, tp, ok = cpu_pairs_per_second(n, L, ppw, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{tp} embed+extract pairs ({ppw} per core x {cores} processes) of the same latent shape, vectorised "
-                         f"numpy/scipy/cryptography port of the reference (oracle/gs_oracle.py); decoded_ok={ok}"}
+                         f"numpy/scipy/cryptography port of the reference (oracle/gs_oracle.py); decoded_ok={ok}",
+               "note": verbatim_reference_note()}
 
     c, h, w = shape
+    ceil_gbs = Be * n * 4 * e2e_steps / ceil_s / 1e9
+    e2e_gbs = Be * n * 4 * e2e_steps / e2e_s / 1e9
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "latents_per_gpu": B, "latent_shape": [c, h, w], "msg_bits": L,
-                   "l2": "inputs larger than L2 (2 x 268 MB streamed per step vs 126 MB L2)" if lat_bytes > 126e6 else
+                   "latents_per_launch": burst_latents, "launches_per_step_per_kernel": n_chunks,
+                   "l2": "inputs larger than L2 (%d MB streamed per step vs 126 MB L2)" % (step_bytes // 1000000) if step_bytes > 2 * 126e6 else
                          "WARNING: working set fits L2", "timing": "CUDA events on the launch stream (the extract stream is forked after the start event and joined before the end event), max over ranks; per-kernel durations: best (ms) and median (ms_median) of 3 bursts of %d back-to-back launches, each burst between one event pair" % inst_steps,
-                   "schedule": "embed and extract of a step run on two CUDA streams and share the SMs (FMA-bound embed next to HBM-bound extract); roofline.step.serial_ms is the same step on one stream",
-                   "uniform_source": "Philox4x32-%d, 23 bits per element" % lib.gswm_philox_rounds(),
+                   "schedule": ("chunked round trip: extract decodes the chunk embed just wrote (noise-free), two buffers, embed of chunk k+1 co-scheduled with extract of chunk k on two CUDA streams"
+                                if pipeline else
+                                "embed and extract of a step run on two CUDA streams and share the SMs (FMA-bound embed next to HBM-bound extract); roofline.step.serial_ms is the same step on one stream"),
+                   "collective": collective,
+                   "uniform_source": "Philox4x32-%d, 23 bits per element, outermost cell refined to 51 bits (uniforms v3)" % lib.gswm_philox_rounds(),
                    "decode_exact": bool(exact), "counters": final},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "decode_exact": bool(e2e_ok),
-                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), %d-latent chunks, 2 slots each" % min(E2E_CHUNK, B),
+                "steps": e2e_steps, "decode_exact": bool(e2e_ok), "checks": e2e_checks, "latents_per_gpu": Be,
+                "path": "gswm_pipe_embed -> pinned host fp32 and pinned host fp32 -> gswm_pipe_extract, two host threads (one per PCIe direction), %d-latent chunks, 2 slots each" % min(E2E_CHUNK, Be),
+                "GBps_each_way_per_gpu": e2e_gbs,
+                "pcie_ceiling_GBps_each_way_per_gpu": ceil_gbs,
+                "pcie_ceiling": "plain pinned cudaMemcpyAsync of the same bytes, H2D and D2H at once, all %d ranks at the same time, this run" % world,
+                "pcie_frac": e2e_gbs / ceil_gbs,
                 "numa_local_cpus": len(local_cpus)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -269,6 +269,19 @@ int gswm_debug_top_cell(const uint32_t* d_words, int64_t n, float* d_out, void* 
  * d_out[n][4].  rounds = 10 is the variant with published known-answer vectors (Random123 kat_vectors). */
 int gswm_debug_philox4x32(const uint32_t* d_in, int64_t n, int32_t rounds, uint32_t* d_out, void* stream);
 
+/* Issue-rate microbenchmark for one instruction class of the embed kernel (bench.py's issue-utilisation denominators,
+ * measured in the same run): warp instructions per clock per SM sub-partition, and the SM clock (GHz) during the run.
+ * Allocates and frees its own scratch buffers and synchronises the device: a measurement tool, not a codec entry point. */
+enum {
+  GSWM_ISSUE_FFMA2 = 0,      /* packed fp32x2 FMA (polynomial)           */
+  GSWM_ISSUE_IMAD_WIDE = 1,  /* 32 x 32 -> 64 multiply (Philox)          */
+  GSWM_ISSUE_LOP3 = 2,       /* three-input logic                        */
+  GSWM_ISSUE_MUFU = 3,       /* MUFU.LG2                                 */
+  GSWM_ISSUE_FFMA_IMM = 4,   /* scalar FMA, immediate operands: the one-instruction-per-clock issue peak */
+  GSWM_ISSUE_PHILOX_MIX = 5  /* IMAD.WIDE + LOP3 alternating             */
+};
+int gswm_debug_issue_rate(int32_t kind, double* warp_inst_per_clk_per_smsp, double* sm_ghz);
+
 /* Number of kernels the library has launched in this process (all entry points); for bench.py. */
 int64_t gswm_launch_count(void);
 
