@@ -90,6 +90,7 @@ struct EmbedArgs {
   uint32_t seed_lo, seed_hi, off_lo, off_hi;   // off_hi holds (offset_hi << 2): its low 2 bits select the Philox call
   uint32_t keys_in_flight;   // GSWM_JOB_KEYS_IN_FLIGHT: read key material only behind the grid dependency wait
   PhiloxKeys rk;             // round keys of (seed_lo, seed_hi)
+  PhiloxLaunch pl;           // round-1 products of the v4 counter layout (constants of the launch)
 };
 
 // Staging for the injected-uniform kernel, grid = (n_latents, tiles_per_latent): blockIdx.x = latent, blockIdx.y = tile.
@@ -112,12 +113,24 @@ __device__ __forceinline__ void build_sign_lut(float4* lut) {
 #define GSWM_TOPCELL 1      // 1: the outermost grid cell is refined (uniforms v3); 0: diagnostic build without (the cell's midpoint)
 #endif
 struct TopCellShared {      // the CTA's log of outermost-cell elements (gswm_math.cuh: TopCellLog)
-  float* list[kTopCellSlots];
+  uint2 list[kTopCellSlots];
   uint32_t count;
 };
 #ifndef GSWM_PHILOX_CONST_KEYS
 #define GSWM_PHILOX_CONST_KEYS 1
 #endif
+#ifndef GSWM_CTR_V4
+#define GSWM_CTR_V4 1       // 1: lane index in counter word 1 (uniforms v4, gswm_math.cuh: philox4x32_v4_calls3); 0: in word 0 (v3)
+#endif
+// v4 counters: the part of a super-iteration's three Philox calls that does not depend on the lane, tabulated per CTA.
+//   shared key : entry ((it % kUniIters) * 2 + (sidx - s0)) * 3 + call for the CTA's it-th latent; refilled every kUniIters
+//                latents (one barrier pair per 42 latents; the first fill happens in the prologue, ahead of the grid
+//                dependency wait).
+//   per-latent : entry sidx * 3 + call of the CTA's current latent, filled next to its keystream.
+constexpr uint32_t kUniIters = 42;
+constexpr uint32_t kUniEntries = kUniIters * 2 * 3;                   // 252 entries, one thread each
+static_assert(kUniEntries <= kThreads && kUniEntries >= 12, "one thread per table entry");
+
 // One SUPER-ITERATION of a tile: 1024 float4 = 4 per thread, fed by three Philox calls.
 // Philox counter word 0..1: G = ((global_latent * tiles + tile) * 4 + sidx) * 256 + tid; words 2..3: offset, call index.
 // kHoisted (shared key, whole tile): the bucket nibbles of this thread's four float4 never change from latent to latent, so
@@ -127,7 +140,14 @@ template <bool kGuard, bool kHoisted = false>
 __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const uint8_t* __restrict__ s_bytes,
                                                       const float4* __restrict__ my_sign, float4* __restrict__ out4,
                                                       uint64_t g_tile, uint32_t sidx, uint32_t n_f4, TopCellShared* s_top,
-                                                      uint32_t sign_pack = 0) {
+                                                      const uint4* __restrict__ uni, uint32_t latent_rel, uint32_t sign_pack = 0) {
+#if GSWM_CTR_V4
+  // g_tile = (global latent * tiles + tile) * 4, warp-uniform; T = g_tile + sidx < 2^54 (checked by the host)
+  const uint64_t T = g_tile + sidx;
+  uint4 cc[3];
+  philox4x32_v4_calls3(cc, threadIdx.x | ((uint32_t)T << 8), uni, a.pl, a.rk);
+  const uint4 c0 = cc[0], c1 = cc[1], c2 = cc[2];
+#else
   const uint64_t g = g_tile + (uint64_t)sidx * kThreads;
   const uint32_t glo = (uint32_t)g, ghi = (uint32_t)(g >> 32);
 #if GSWM_PHILOX_CONST_KEYS
@@ -138,6 +158,7 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
   const uint4 c0 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 0u), a.seed_lo, a.seed_hi);
   const uint4 c1 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 1u), a.seed_lo, a.seed_hi);
   const uint4 c2 = philox4x32(make_uint4(glo, ghi, a.off_lo, a.off_hi + 2u), a.seed_lo, a.seed_hi);
+#endif
 #endif
   const uint32_t i0 = (4u * sidx) * kThreads + threadIdx.x;
   const uint32_t f0[4] = {fbits_top23(c0.x), fbits_top23(c0.y), fbits_top23(c0.z), fbits_top23(c0.w)};
@@ -156,7 +177,7 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
 #endif
     // uniforms v3: an element in the outermost grid cell is logged here and refined in the kernel's epilogue
 #if GSWM_TOPCELL
-    const TopCellLog top{&s_top->count, s_top->list, reinterpret_cast<float*>(out4 + i)};
+    const TopCellLog top{&s_top->count, s_top->list, latent_rel, i};
 #else
     const NoTopCell top;                                               // diagnostic build (uniforms v2: the cell's midpoint)
 #endif
@@ -188,6 +209,10 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
 #ifndef GSWM_EMBED_MINB
 #define GSWM_EMBED_MINB 4
 #endif
+#ifndef GSWM_PL_UNROLL
+#define GSWM_PL_UNROLL 2    // super-iterations of a per-latent-key CTA unrolled together
+#endif
+constexpr int kPlUnroll = GSWM_PL_UNROLL;
 #ifndef GSWM_EMBED_MINB_PER_LATENT
 #define GSWM_EMBED_MINB_PER_LATENT 6
 #endif
@@ -215,6 +240,11 @@ embed_kernel(const EmbedArgs a) {
   __shared__ __align__(16) float4 s_sign[512];
   __shared__ __align__(16) float4 s_sign16[16];                       // nibble -> +-1.0f x4 (shared-key whole-tile path)
   __shared__ __align__(16) TopCellShared s_top;                       // outermost-cell elements seen by this CTA (refined in the epilogue)
+#if GSWM_CTR_V4
+  __shared__ __align__(16) uint4 s_uni[kUniEntries];                  // lane-independent halves of Philox rounds 1..3 (philox_v4_cta_part)
+#else
+  uint4* const s_uni = nullptr;
+#endif
   const uint32_t tile = kPerLatent ? blockIdx.y : blockIdx.y >> 1;
   const uint32_t tiles = a.tiles_per_latent;
   const uint32_t words = tile_words(a.n_elems, tile);
@@ -245,10 +275,18 @@ embed_kernel(const EmbedArgs a) {
   trace_mark(1);
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
   const float4* my_sign = s_sign + (threadIdx.x & 1u);               // i & 1 == threadIdx.x & 1 for every float4
+#if GSWM_CTR_V4
+  const uint64_t tile_stride = 4ull;                                  // super-iterations per tile (the lane index lives in another counter word)
+#else
   const uint64_t tile_stride = 4ull * kThreads;                       // Philox counters per tile
+#endif
   const uint64_t n_f4_latent = (uint64_t)(a.n_elems >> 2);
   float4* out4 = reinterpret_cast<float4*>(a.out) + (blockIdx.x * n_f4_latent + (uint64_t)tile * kTileF4);
+#if GSWM_CTR_V4
+  uint64_t g_tile = ((uint64_t)(a.first_latent + blockIdx.x) * tiles + tile) * tile_stride;
+#else
   uint64_t g_tile = ((uint64_t)(a.first_latent + blockIdx.x) * tiles + tile) * tile_stride + threadIdx.x;
+#endif
   const uint64_t out_step = gridDim.x * n_f4_latent;
   const uint64_t g_step = (uint64_t)gridDim.x * tiles * tile_stride;
 
@@ -259,6 +297,25 @@ embed_kernel(const EmbedArgs a) {
     // because the warp schedulers share an SM unfairly and the CTAs of one launch finish anywhere between 27 and 60 us
     // -- tools/embed_trace.py -- but same-address atomics under this kernel's store traffic complete only every ~34 ns,
     // far too slow for one grab per latent: 67.6 us against 56.1 us.)
+#if GSWM_CTR_V4
+    // entry e = (it * 2 + sd) * 3 + call of the table, for the kUniIters latents starting at the CTA's `it0`-th
+    auto fill_uni = [&](uint64_t g_tile_first) {
+      const uint32_t e = threadIdx.x;
+      if (e < kUniEntries) {
+        const uint64_t T = g_tile_first + (uint64_t)(e / 6u) * g_step + s0 + (e % 6u) / 3u;
+        s_uni[e] = philox_v4_cta_part(((uint32_t)(T >> 24) << 2) | (e % 3u), a.pl, a.rk);
+      }
+    };
+    fill_uni(g_tile);                                                 // (registers and kernel parameters only: could sit ahead of the wait)
+    __syncthreads();
+    uint32_t it = 0;
+#define GSWM_UNI_STEP()                                                                                    \
+    if (++it == kUniIters) { __syncthreads(); fill_uni(g_tile + g_step); __syncthreads(); it = 0; }
+#define GSWM_UNI(sd) (s_uni + (it * 2u + (sd)) * 3u)
+#else
+#define GSWM_UNI_STEP()
+#define GSWM_UNI(sd) nullptr
+#endif
     if (n_f4 == kTileF4) {
       // this thread's eight bucket nibbles (float4 (4 sidx + k) 256 + tid, sidx in {s0, s0 + 1}) are the same for every
       // latent: fetched once, kept as table offsets (nibble << 4) in the bytes of two registers
@@ -271,26 +328,37 @@ embed_kernel(const EmbedArgs a) {
         pack[j >> 2] |= (nib << 4) << (8u * (j & 3u));
       }
       for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
-        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0, n_f4, &s_top, pack[0]);
-        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0 + 1, n_f4, &s_top, pack[1]);
+        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0, n_f4, &s_top, GSWM_UNI(0), (uint32_t)latent, pack[0]);
+        embed_super_iteration<false, true>(a, s_bytes, s_sign16, out4, g_tile, s0 + 1, n_f4, &s_top, GSWM_UNI(1), (uint32_t)latent, pack[1]);
+        GSWM_UNI_STEP()
       }
     } else {
       for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
-        embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4, &s_top);
-        if ((s0 + 1) * 4 * kThreads < n_f4) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4, &s_top);
+        embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0, n_f4, &s_top, GSWM_UNI(0), (uint32_t)latent);
+        if ((s0 + 1) * 4 * kThreads < n_f4) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, s0 + 1, n_f4, &s_top, GSWM_UNI(1), (uint32_t)latent);
+        GSWM_UNI_STEP()
       }
     }
+#undef GSWM_UNI_STEP
+#undef GSWM_UNI
     trace_mark(3);
   } else {
     for (int64_t latent = blockIdx.x; latent < a.n_latents; latent += gridDim.x, out4 += out_step, g_tile += g_step) {
       __syncthreads();                                                // previous latent's readers are done with s_ks (first pass: LUT built)
+#if GSWM_CTR_V4
+      if (threadIdx.x >= 32 && threadIdx.x < 44) {                    // warp 1, next to warp 0's ChaCha20: entry sidx * 3 + call
+        const uint32_t e = threadIdx.x - 32u;
+        const uint64_t T = g_tile + e / 3u;
+        s_uni[e] = philox_v4_cta_part(((uint32_t)(T >> 24) << 2) | (e % 3u), a.pl, a.rk);
+      }
+#endif
       compute_private_slice(s_ks, a.keys, a.nonces, a.msgs + latent * (int64_t)a.msg_stride_bytes, latent, tile, words,
                             a.msg_words, a.tiled_words);
       if (n_f4 == kTileF4) {
-#pragma unroll 2
-        for (uint32_t sidx = 0; sidx < 4; ++sidx) embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4, &s_top);
+#pragma unroll kPlUnroll
+        for (uint32_t sidx = 0; sidx < 4; ++sidx) embed_super_iteration<false>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4, &s_top, s_uni + 3u * sidx, (uint32_t)latent);
       } else {
-        for (uint32_t sidx = 0; sidx * 4 * kThreads < n_f4; ++sidx) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4, &s_top);
+        for (uint32_t sidx = 0; sidx * 4 * kThreads < n_f4; ++sidx) embed_super_iteration<true>(a, s_bytes, my_sign, out4, g_tile, sidx, n_f4, &s_top, s_uni + 3u * sidx, (uint32_t)latent);
       }
     }
   }
@@ -299,14 +367,22 @@ embed_kernel(const EmbedArgs a) {
   __syncthreads();                                                    // all stores and log entries of the CTA are done and visible to it
   const uint32_t logged = s_top.count < kTopCellSlots ? s_top.count : kTopCellSlots;
   for (uint32_t e = threadIdx.x; e < logged; e += kThreads) {
-    float* where = s_top.list[e];
-    const uint64_t idx = (uint64_t)(where - a.out);                   // element index within this launch's output
-    const uint64_t lat = idx / (uint64_t)a.n_elems;
-    const uint32_t el = (uint32_t)(idx - lat * (uint64_t)a.n_elems);  // ... within its latent
-    const uint32_t t = el / kTileElems, f4 = (el % kTileElems) >> 2;  // tile; float4 (4 sidx + k) * 256 + tid within the tile
-    const uint32_t sk = f4 / kThreads;
-    const uint64_t g = (((uint64_t)a.first_latent + lat) * tiles + t) * tile_stride + (uint64_t)(sk >> 2) * kThreads + f4 % kThreads;
-    top_cell_fixup(where, g, 4u * (sk & 3u) + (el & 3u), a.off_lo, a.off_hi, a.seed_lo, a.seed_hi);
+    const uint64_t lat = s_top.list[e].x;                             // latent within this launch
+    const uint32_t t = tile, f4 = s_top.list[e].y;                    // tile; float4 (4 sidx + k) * 256 + tid within the tile
+    float4* where = reinterpret_cast<float4*>(a.out) + (lat * n_f4_latent + (uint64_t)t * kTileF4 + f4);
+    const uint32_t sk = f4 / kThreads, tid = f4 % kThreads;
+#if GSWM_CTR_V4
+    const uint64_t T = (((uint64_t)a.first_latent + lat) * tiles + t) * 4u + (sk >> 2);
+    uint4 ctr = make_uint4(a.off_lo, tid | ((uint32_t)T << 8), a.off_hi, (uint32_t)(T >> 24) << 2);
+#else
+    const uint64_t g = (((uint64_t)a.first_latent + lat) * tiles + t) * tile_stride + (uint64_t)(sk >> 2) * kThreads + tid;
+    uint4 ctr = make_uint4((uint32_t)g, (uint32_t)(g >> 32), a.off_lo, a.off_hi);
+#endif
+    uint4 w[3];
+#pragma unroll 1
+    for (uint32_t c = 0; c < 3; ++c) w[c] = philox4x32(make_uint4(ctr.x, ctr.y, ctr.z, ctr.w + c), a.seed_lo, a.seed_hi);
+    ctr.w += 3u;
+    top_cell_fixup(where, w, sk & 3u, ctr, a.seed_lo, a.seed_hi);
   }
 #endif
 }
@@ -1072,7 +1148,19 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
   a.out = d_out;
   a.first_latent = first_latent;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+#if GSWM_CTR_V4
+  a.off_lo = (uint32_t)offset; a.off_hi = (uint32_t)(offset >> 32);
+  {
+    const unsigned __int128 last = ((unsigned __int128)first_latent + (unsigned __int128)job->n_latents) * a.tiles_per_latent * 4u;
+    if (last >> 54) return GSWM_E_RANGE;                              // the counter holds 54 bits of (latent, tile, super-iteration)
+    const uint64_t pa = 0xD2511F53ull * a.off_lo, pb = 0xCD9E8D57ull * a.off_hi;
+    a.pl.a_hi = (uint32_t)(pa >> 32); a.pl.b_lo = (uint32_t)pb;
+    a.pl.x0 = (uint32_t)(pb >> 32) ^ a.seed_lo;                       // round keys 0: (seed_lo, seed_hi)
+    a.pl.x3 = (uint32_t)pa ^ (a.seed_hi + 0xBB67AE85u);               // round keys 1, word 1
+  }
+#else
   a.off_lo = (uint32_t)offset; a.off_hi = (uint32_t)(offset >> 32) << 2;
+#endif
   for (int r = 0; r < GSWM_PHILOX_ROUNDS; ++r) {
     a.rk.k[2 * r] = a.seed_lo + (uint32_t)r * 0x9E3779B9u;
     a.rk.k[2 * r + 1] = a.seed_hi + (uint32_t)r * 0xBB67AE85u;

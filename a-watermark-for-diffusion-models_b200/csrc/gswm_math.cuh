@@ -19,6 +19,10 @@ namespace gswm {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int n) { return __funnelshift_l(x, x, n); }
 
+#ifndef GSWM_CHACHA_UNROLL
+#define GSWM_CHACHA_UNROLL 2     // double rounds unrolled together: code size counts (per-latent keys: 64.4 us with 2 against 69.0 us fully unrolled -- the CTAs of an SM sit in different parts of the kernel and share its instruction cache)
+#endif
+constexpr int kChachaUnroll = GSWM_CHACHA_UNROLL;
 #define GSWM_QR(a, b, c, d)            \
   a += b; d ^= a; d = rotl32(d, 16);   \
   c += d; b ^= c; b = rotl32(b, 12);   \
@@ -36,7 +40,7 @@ __device__ __forceinline__ void chacha20_block(const uint32_t (&key)[8], const u
   uint32_t x4 = key[0], x5 = key[1], x6 = key[2], x7 = key[3];
   uint32_t x8 = key[4], x9 = key[5], x10 = key[6], x11 = key[7];
   uint32_t x12 = ctr_lo, x13 = ctr_hi, x14 = nonce[2], x15 = nonce[3];
-#pragma unroll
+#pragma unroll kChachaUnroll
   for (int r = 0; r < 10; ++r) {
     GSWM_QR(x0, x4, x8, x12) GSWM_QR(x1, x5, x9, x13) GSWM_QR(x2, x6, x10, x14) GSWM_QR(x3, x7, x11, x15)
     GSWM_QR(x0, x5, x10, x15) GSWM_QR(x1, x6, x11, x12) GSWM_QR(x2, x7, x8, x13) GSWM_QR(x3, x4, x9, x14)
@@ -100,6 +104,58 @@ __device__ __forceinline__ uint4 philox4x32_keys(uint4 c, const PhiloxKeys& rk) 
     c = n;
   }
   return c;
+}
+
+// Three Philox4x32 calls for one super-iteration under the v4 counter layout (see "The product's uniform source" below):
+//   ctr = (offset_lo, c1, offset_hi, c3),  c1 = tid | (T & 0xFFFFFF) << 8,  c3 = (T >> 24) << 2 | call,  call = 0..2
+// with T = (global latent * tiles + tile) * 4 + super-iteration: the only word that differs from lane to lane is c1, and
+// c1 is not multiplied in round 1.  Evaluated as written this is plain Philox4x32-R on those counters; evaluated with
+// the data flow in mind, what does not depend on the lane is computed ONCE PER CTA (philox_v4_cta_part: a table in shared
+// memory filled ahead of the latent loop, read back with one broadcast LDS.128 per call), and what depends on the lane
+// but not on the call is shared by the three calls:
+//   round 1: both products are constants of the launch (M0 * offset_lo, M1 * offset_hi, host-computed: PhiloxLaunch);
+//   round 2: M0 * x is one multiply for all three calls; M1 * z does not depend on the lane (table);
+//   round 3: M0 * x does not depend on the lane (table); M1 * z is one multiply for all three calls;
+//   rounds 4..R: two multiplies per call.
+// 2 + 6 (R - 3) = 26 IMAD.WIDE per lane for R = 7 instead of 35 with the lane index in word 0 (v3: 1 + 4 + 6 (R - 2)), and
+// 9 fewer LOP3 -- about a tenth of the embed kernel's FMA-heavy-pipe time, the pipe that bounds it.  (Left to the
+// compiler, the lane-independent products stay vector IMAD.WIDE -- it does not move them to the uniform datapath -- and
+// nothing is gained: 68 IMAD.WIDE per 8 float4 either way, tools/sass_loop_hist.py.)
+struct PhiloxLaunch {
+  uint32_t a_hi;            // hi(M0 * offset_lo)
+  uint32_t b_lo;            // lo(M1 * offset_hi)
+  uint32_t x0;              // hi(M1 * offset_hi) ^ round key 0 (word 0)
+  uint32_t x3;              // lo(M0 * offset_lo) ^ round key 1 (word 1)     [rk.k[3]]
+};
+// Lane-independent part of rounds 1..3 for counter word 3 = c3: {m1 ^ k4, hi(q) ^ k5, lo(q), -}
+__device__ __forceinline__ uint4 philox_v4_cta_part(uint32_t c3, const PhiloxLaunch& L, const PhiloxKeys& rk) {
+  const uint32_t n2 = L.a_hi ^ c3 ^ rk.k[1];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * n2;
+  const uint32_t m0 = (uint32_t)(p1 >> 32) ^ L.b_lo ^ rk.k[2];
+  const uint64_t q = (uint64_t)0xD2511F53u * m0;
+  return make_uint4((uint32_t)p1 ^ rk.k[4], (uint32_t)(q >> 32) ^ rk.k[5], (uint32_t)q, 0u);
+}
+// uni[call]: the table entries of this super-iteration (shared memory, same address for every lane)
+__device__ __forceinline__ void philox4x32_v4_calls3(uint4 (&out)[3], uint32_t c1, const uint4* __restrict__ uni,
+                                                     const PhiloxLaunch& L, const PhiloxKeys& rk) {
+  static_assert(GSWM_PHILOX_ROUNDS >= 3, "the shared evaluation covers rounds 1..3");
+  const uint32_t n0 = L.x0 ^ c1;                                      // round 1, word 0
+  const uint64_t p0 = (uint64_t)0xD2511F53u * n0;                     // round 2
+  const uint32_t m2 = (uint32_t)(p0 >> 32) ^ L.x3;
+  const uint32_t m3 = (uint32_t)p0;
+  const uint64_t p1s = (uint64_t)0xCD9E8D57u * m2;                    // round 3
+#pragma unroll
+  for (uint32_t call = 0; call < 3; ++call) {
+    const uint4 u = uni[call];
+    uint4 c = make_uint4((uint32_t)(p1s >> 32) ^ u.x, (uint32_t)p1s, u.y ^ m3, u.z);
+#pragma unroll
+    for (int r = 3; r < GSWM_PHILOX_ROUNDS; ++r) {
+      const uint64_t x0 = (uint64_t)0xD2511F53u * c.x;
+      const uint64_t x1 = (uint64_t)0xCD9E8D57u * c.z;
+      c = make_uint4((uint32_t)(x1 >> 32) ^ c.y ^ rk.k[2 * r], (uint32_t)x1, (uint32_t)(x0 >> 32) ^ c.w ^ rk.k[2 * r + 1], (uint32_t)x0);
+    }
+    out[call] = c;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,38 +297,48 @@ __device__ __forceinline__ float top_cell_quantile(uint32_t w) {
 }
 struct NoTopCell {                                                   // test hook / callers without a counter: the cell keeps its midpoint
   static constexpr bool kLogs = false;
-  __device__ __forceinline__ void operator()(uint32_t) const {}
+  __device__ __forceinline__ void operator()() const {}
 };
 // How the outermost cell gets refined without costing the hot loop anything.  Tried first, and measured (4096 SD-2.1
 // latents, profiles/r02b_kbench.jsonl): the refinement inline in the patch block -- 69.6 us against 55.0 us, the loop body
 // (2561 instructions, every patch block dragging a Philox call behind it) no longer fits the instruction cache, and what
 // the hot path jumps over is fetched all the same; the rare formulas as out-of-line calls -- 58.2 .. 59.4 us, a call in
 // the loop makes the compiler re-materialise its constants after every patch block; a per-thread mask tested after each
-// super-iteration -- 58.5 us.  What costs nothing: the patch block appends the ADDRESS of such an element to a small
-// list in SHARED memory (one atomic and one store inside an already rare block) and the CTA walks the list once, after
-// its last latent.  A CTA sees one such element per 8.4 M it produces; the list holds 64 (an overflowing
-// element would keep the cell's midpoint -- still a sample of the right bucket).
+// super-iteration -- 58.5 us.  What costs nothing: the patch block -- which ~15 % of the warps' float4 enter anyway -- takes
+// the minimum of its four x once more, and a float4 holding such an element (one in 2 M) appends its POSITION to a small
+// list in SHARED memory; the CTA walks the list once, after its last latent, re-derives the float4's Philox counter from
+// the position, finds the element(s) with m = 2^23 - 1 and refines them.  The list holds 64 float4 (a CTA sees one per
+// 2 M float4 it produces; an overflowing one would keep the cell's midpoint -- still a sample of the right bucket).
 constexpr uint32_t kTopCellSlots = 64;
 struct TopCellLog {
   static constexpr bool kLogs = true;
   uint32_t* count;          // shared memory
-  float** list;             // shared memory, kTopCellSlots entries: the ADDRESS of the element says everything (which latent,
-                            // tile, super-iteration, lane, position -- hence which Philox counter), so that is all that is logged
-  float* out_f4;            // address of the float4 being produced
-  __device__ __forceinline__ void operator()(uint32_t j) const {
+  uint2* list;              // shared memory, kTopCellSlots entries: (latent within the launch, float4 within the tile) -- with the
+                            // CTA's tile that says everything (which super-iteration, lane, position: hence which Philox counter
+                            // and which address).  Both are values the loop has anyway (a uniform register and a constant + tid):
+                            // logging the float4's ADDRESS instead kept two more registers alive across the polynomial
+                            // (per-latent keys, 40 registers: 12 bytes of spills, 69.4 us against 63.1 us).
+  uint32_t latent, f4;
+  __device__ __forceinline__ void operator()() const {
     const uint32_t slot = atomicAdd(count, 1u);
-    if (slot < kTopCellSlots) list[slot] = out_f4 + j;
+    if (slot < kTopCellSlots) list[slot] = make_uint2(latent, f4);
   }
 };
-// The epilogue's half.  `idx`: the element's index in the launch's output, `g`: Philox counter words 0..1 of its
-// super-iteration, kj = 4 k + j (element j of float4 k): word j of Philox call 3 of that counter under key
-// (seed_lo, seed_hi + k) -> |z|; the sign is the one the element was stored with.
-__device__ __forceinline__ void top_cell_fixup(float* where, uint64_t g, uint32_t kj, uint32_t off_lo, uint32_t off_hi,
-                                               uint32_t seed_lo, uint32_t seed_hi) {
-  const uint4 r = philox4x32(make_uint4((uint32_t)g, (uint32_t)(g >> 32), off_lo, off_hi + 3u), seed_lo, seed_hi + (kj >> 2));
-  const uint32_t j = kj & 3u;
-  const float mag = top_cell_quantile(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
-  *where = copysignf(mag, *where);
+// The epilogue's half: float4 k of the super-iteration whose three Philox outputs are w[0..2] (recomputed by the caller
+// from the address), `ctr3` = that super-iteration's counter with call index 3.  Every element of the float4 with
+// m = 2^23 - 1 gets |z| from word j of Philox(ctr3) under key (seed_lo, seed_hi + k); the sign is the one it was stored with.
+__device__ __forceinline__ void top_cell_fixup(float4* where, const uint4 (&w)[3], uint32_t k, uint4 ctr3, uint32_t seed_lo,
+                                               uint32_t seed_hi) {
+  const uint32_t w0[4] = {w[0].x, w[0].y, w[0].z, w[0].w}, w1[4] = {w[1].x, w[1].y, w[1].z, w[1].w}, w2[4] = {w[2].x, w[2].y, w[2].z, w[2].w};
+  const uint4 r = philox4x32(ctr3, seed_lo, seed_hi + k);
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  float* z = reinterpret_cast<float*>(where);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t fb = k == 0 ? fbits_top23(w0[j]) : k == 1 ? fbits_top23(w1[j]) : k == 2 ? fbits_top23(w2[j])
+                                                                                         : fbits_low_bytes(w0[j], w1[j], w2[j]);
+    if (fb == 0x3FFFFFFFu) z[j] = copysignf(top_cell_quantile(rr[j]), z[j]);
+  }
 }
 constexpr float kTopCellX = -18.5f;
 
@@ -322,14 +388,12 @@ __device__ __forceinline__ float4 bucket_quantile4_f32(uint32_t f0, uint32_t f1,
   if (__builtin_expect(any_tail, 0)) {
     // per element the decision is its own x (the f bit patterns are dead by now: nothing is kept alive across the Horner
     // chains for this block); the outermost cell is x < -18.5 (m = 2^23 - 1: x = -19.0; m = 2^23 - 2: x = -17.4)
-    auto patch = [&](uint32_t j, float x) {
-      if (TopCell::kLogs && x < kTopCellX) top(j);                    // outermost cell: noted for the epilogue, midpoint for now
-      return quantile_tail(x);
-    };
-    if (x01.x < GSWM_HNQ_XSPLIT) g01.x = patch(0, x01.x);
-    if (x01.y < GSWM_HNQ_XSPLIT) g01.y = patch(1, x01.y);
-    if (x23.x < GSWM_HNQ_XSPLIT) g23.x = patch(2, x23.x);
-    if (x23.y < GSWM_HNQ_XSPLIT) g23.y = patch(3, x23.y);
+    if (x01.x < GSWM_HNQ_XSPLIT) g01.x = quantile_tail(x01.x);
+    if (x01.y < GSWM_HNQ_XSPLIT) g01.y = quantile_tail(x01.y);
+    if (x23.x < GSWM_HNQ_XSPLIT) g23.x = quantile_tail(x23.x);
+    if (x23.y < GSWM_HNQ_XSPLIT) g23.y = quantile_tail(x23.y);
+    // outermost cell somewhere in this float4: noted for the epilogue, midpoint for now
+    if (TopCell::kLogs && fminf(fminf(x01.x, x01.y), fminf(x23.x, x23.y)) < kTopCellX) top();
   }
 #endif
 #ifdef GSWM_WHATIF_NOSIGN

@@ -33,6 +33,7 @@ UNIT = "latents/s"
 SHAPES = {"sd21": (4, 64, 64), "sdxl": (4, 128, 128)}
 SIGMA = 0.325
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+NCU_SUMMARY = {"embed_kernel": "r02h_embed_shared_ncu_summary.json", "extract_kernel": "r02h_extract_f32_ncu_summary.json"}
 E2E_CHUNK = 4096              # latents per pipe chunk.  The kernels take ~0.1 ms of a ~5.5 ms PCIe-bound step, so there is nothing to
                               # gain from overlapping them with the copies, while every extra copy costs ~65 us when both PCIe
                               # directions are busy (tools/e2ebench.py: 7.4 / 6.5 / 6.0 / 5.65 ms at 64 / 256 / 1024 / 4096 latents)
@@ -278,7 +279,7 @@ def ncu_pipe_summary(kernel):
     """Issue / pipe utilisation of `kernel` from the committed ncu --set full capture (profiles/), for the roofline block:
     the embed kernel is bound by the FMA pipes, not by HBM, and these are the numbers that say so."""
     try:
-        with open(os.path.join(ROOT, "profiles", f"r01h_{kernel.split('_')[0]}_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", NCU_SUMMARY[kernel])) as f:
             k = json.load(f)["kernels"][0]
         pick = {"issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
                 "fma_heavy_pipe_pct": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
@@ -286,7 +287,7 @@ def ncu_pipe_summary(kernel):
                 "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
                 "duration_us_under_ncu": "gpu__time_duration.sum"}
         out = {a: round(float(k[b]["value"]), 2) for a, b in pick.items()}
-        out["source"] = f"profiles/r01h_{kernel.split('_')[0]}_ncu_summary.json (cold, serialised launch)"
+        out["source"] = f"profiles/{NCU_SUMMARY[kernel]} (cold, serialised launch)"
         return out
     except Exception:  # noqa: BLE001
         return None
@@ -322,7 +323,7 @@ def verbatim_reference_note():
 def embed_issue_profile():
     """Executed warp instructions per latent element of the embed kernel, from the committed ncu capture of this build
     (smsp__inst_executed.sum / elements): a property of the binary, not of the run."""
-    for name in ("r02_embed_ncu_summary.json", "r01h_embed_ncu_summary.json"):
+    for name in ("r02h_embed_shared_ncu_summary.json", "r01h_embed_ncu_summary.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 k = json.load(f)["kernels"][0]
@@ -623,6 +624,12 @@ def run_gpu_arm(args):
         _, _, _, h_cnt, h_flags = e2e_step()
     e2e_s = time.perf_counter() - t0
     barrier()
+    e2e_checks = {"all_messages_exact": int(h_cnt[2]) == Be and int(h_cnt[0]) == Be * L, "none_rejected": not bool(h_flags.any())}
+    # the embedded latents that came back over PCIe must be the ones the resident path produced
+    chk = torch.empty((min(8, Be), *shape), dtype=torch.float32, device=dev)
+    cj = gswm._lib.Job(chk.shape[0], n, L, dj_all.job.flags, dj_all.job.keys, dj_all.job.nonces, dj_all.job.msgs)
+    gswm._lib.check(lib.gswm_embed(C.byref(cj), seed, 0, first, chk.data_ptr(), sp), "gswm_embed")
+    e2e_checks["embedded_latents_equal_resident_path"] = bool(torch.equal(h_out[:chk.shape[0]], chk.cpu()))
     # the box's ceiling for exactly this traffic: plain pinned cudaMemcpyAsync of the same bytes, both directions at once,
     # every rank at the same time -- no kernels, no pipe
     d_a = torch.empty((Be, n), dtype=torch.float32, device=dev)
@@ -647,14 +654,7 @@ def run_gpu_arm(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s, ceil_s = te.cpu().tolist()
     e2e_value = Be * world * e2e_steps / e2e_s
-    e2e_checks = {"all_messages_exact": int(h_cnt[2]) == Be and int(h_cnt[0]) == Be * L, "none_rejected": not bool(h_flags.any())}
     e2e_ok = all(e2e_checks.values())
-    # the embedded latents that came back over PCIe must be the ones the resident path produced
-    chk = torch.empty((min(8, Be), *shape), dtype=torch.float32, device=dev)
-    cj = gswm._lib.Job(chk.shape[0], n, L, dj_all.job.flags, dj_all.job.keys, dj_all.job.nonces, dj_all.job.msgs)
-    gswm._lib.check(lib.gswm_embed(C.byref(cj), seed, 0, first, chk.data_ptr(), sp), "gswm_embed")
-    e2e_checks["embedded_latents_equal_resident_path"] = bool(torch.equal(h_out[:chk.shape[0]], chk.cpu()))
-    e2e_ok = e2e_ok and e2e_checks["embedded_latents_equal_resident_path"]
     key_bytes = kme.keys.nbytes + kme.nonces.nbytes + (kme.msgs.nbytes if kme.msgs is not None else 0)
     h2d = Be * n * 4 + key_bytes * 2                  # latents in + key material once per pipe call
     d2h = Be * n * 4 + Be * (L // 8) + Be * 4 + Be + 8 * NC
@@ -732,7 +732,7 @@ def run_gpu_arm(args):
                                 if pipeline else
                                 "embed and extract of a step run on two CUDA streams and share the SMs (FMA-bound embed next to HBM-bound extract); roofline.step.serial_ms is the same step on one stream"),
                    "collective": collective,
-                   "uniform_source": "Philox4x32-%d, 23 bits per element, outermost cell refined to 51 bits (uniforms v3)" % lib.gswm_philox_rounds(),
+                   "uniform_source": "Philox4x32-%d, 23 bits per element, outermost cell refined to 51 bits (uniforms v4)" % lib.gswm_philox_rounds(),
                    "decode_exact": bool(exact), "counters": final},
         "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -238,32 +238,36 @@ GSWM_TILE = 16384          # elements per tile (32 ChaCha blocks) -- the kernels
 GSWM_PHILOX_ROUNDS = 7           # csrc/gswm_math.cuh default (Philox4x32-7, the fewest Crush-resistant rounds)
 
 
+def _gswm_counters(offset: int, latent_index: int, tiles: int, tile, s_, tid, call: int) -> np.ndarray:
+    """Philox counters of "gswm uniforms v4" for arrays tile / s_ / tid (uint64) and one call index:
+        T = (latent_index * tiles_per_latent + tile) * 4 + s        (< 2^54)
+        ctr = (offset_lo, tid | (T & 0xFFFFFF) << 8, offset_hi, (T >> 24) << 2 | call)
+    The lane index sits in word 1, which the first round does not multiply (csrc/gswm_math.cuh: philox4x32_v4_calls3)."""
+    T = (np.uint64(latent_index * tiles) + tile) * np.uint64(4) + s_
+    ctr = np.empty((T.size, 4), dtype=np.uint32)
+    ctr[:, 0] = offset & 0xFFFFFFFF
+    ctr[:, 1] = (tid | ((T & np.uint64(0xFFFFFF)) << np.uint64(8))).astype(np.uint32)
+    ctr[:, 2] = (offset >> 32) & 0xFFFFFFFF
+    ctr[:, 3] = ((((T >> np.uint64(24)) << np.uint64(2)) | np.uint64(call)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    return ctr
+
+
 def gswm_uniform_ints(seed: int, offset: int, latent_index: int, n_elems: int,
                       rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
-    """The 23-bit integer m of every element of one latent ("gswm uniforms v3", csrc/gswm_math.cuh).
+    """The 23-bit integer m of every element of one latent ("gswm uniforms v4", csrc/gswm_math.cuh).
 
     The latent is cut into tiles of 16384 elements; a tile into 4 super-iterations of 256 lanes; lane `tid`
     of super-iteration `s` owns the four float4 (16 elements) at within-tile float4 indices
-    (4s + k) * 256 + tid, k = 0..3.  Its Philox counter is
-        G = ((latent_index * tiles_per_latent + tile) * 4 + s) * 256 + tid
-    and three calls W_c = Philox4x32(ctr = (G_lo, G_hi, offset_lo, (offset_hi << 2) + c), key = seed), c = 0..2,
-    feed the 16 elements: float4 k < 3, element j: m = W_k[j] >> 9; float4 3, element j:
+    (4s + k) * 256 + tid, k = 0..3.  Three calls W_c = Philox4x32(ctr(T, tid, c), key = seed), c = 0..2 (counters:
+    _gswm_counters) feed the 16 elements: float4 k < 3, element j: m = W_k[j] >> 9; float4 3, element j:
     m = (W_0[j] & 0xFF) | (W_1[j] & 0xFF) << 8 | (W_2[j] & 0x7F) << 16.
     """
     tiles = (n_elems + GSWM_TILE - 1) // GSWM_TILE
     t, s_, tid = np.meshgrid(np.arange(tiles, dtype=np.uint64), np.arange(4, dtype=np.uint64),
                              np.arange(256, dtype=np.uint64), indexing="ij")
-    g = ((np.uint64(latent_index * tiles) + t) * np.uint64(4) + s_) * np.uint64(256) + tid      # (tiles, 4, 256)
-    g = g.reshape(-1)
-    ctr = np.empty((g.size, 4), dtype=np.uint32)
-    ctr[:, 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
-    ctr[:, 1] = (g >> np.uint64(32)).astype(np.uint32)
-    ctr[:, 2] = offset & 0xFFFFFFFF
+    t, s_, tid = t.reshape(-1), s_.reshape(-1), tid.reshape(-1)
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    w = []
-    for c in range(3):
-        ctr[:, 3] = (((offset >> 32) << 2) + c) & 0xFFFFFFFF
-        w.append(philox4x32(ctr, key, rounds))                        # (tiles*1024, 4)
+    w = [philox4x32(_gswm_counters(offset, latent_index, tiles, t, s_, tid, c), key, rounds) for c in range(3)]   # (tiles*1024, 4)
     m = np.empty((tiles, 4, 4, 256, 4), dtype=np.uint32)            # [tile][s][k][tid][j]
     for k in range(3):
         m[:, :, k] = (w[k] >> np.uint32(9)).reshape(tiles, 4, 256, 4)
@@ -273,14 +277,14 @@ def gswm_uniform_ints(seed: int, offset: int, latent_index: int, n_elems: int,
     return m.reshape(-1)[:n_elems]
 
 
-GSWM_TOP_CELL = (1 << 23) - 1   # the outermost grid cell, subdivided by "gswm uniforms v3"
+GSWM_TOP_CELL = (1 << 23) - 1   # the outermost grid cell, subdivided since "gswm uniforms v3"
 
 
 def gswm_top_cell_words(seed: int, offset: int, latent_index: int, n_elems: int, elems: np.ndarray,
                         rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
     """The 32 refinement bits of elements `elems` (flat indices into one latent) should they fall in the outermost cell:
-    word j of Philox4x32(ctr = (G_lo, G_hi, offset_lo, (offset_hi << 2) + 3), key = (seed_lo, seed_hi + k)), where the
-    element is number j of float4 k of the super-iteration with counter G (see gswm_uniform_ints)."""
+    word j of Philox4x32(ctr(T, tid, call = 3), key = (seed_lo, seed_hi + k)), where the element is number j of float4 k
+    of super-iteration T, lane tid (see gswm_uniform_ints)."""
     elems = np.asarray(elems, dtype=np.int64).reshape(-1)
     tiles = (n_elems + GSWM_TILE - 1) // GSWM_TILE
     tile, within = elems // GSWM_TILE, elems % GSWM_TILE
@@ -289,9 +293,8 @@ def gswm_top_cell_words(seed: int, offset: int, latent_index: int, n_elems: int,
     s_, k = sk // 4, sk % 4
     out = np.empty(elems.size, dtype=np.uint32)
     for i in range(elems.size):
-        g = ((latent_index * tiles + int(tile[i])) * 4 + int(s_[i])) * 256 + int(tid[i])
-        ctr = np.array([[g & 0xFFFFFFFF, (g >> 32) & 0xFFFFFFFF, offset & 0xFFFFFFFF, (((offset >> 32) << 2) + 3) & 0xFFFFFFFF]],
-                       dtype=np.uint32)
+        ctr = _gswm_counters(offset, latent_index, tiles, np.array([tile[i]], dtype=np.uint64), np.array([s_[i]], dtype=np.uint64),
+                             np.array([tid[i]], dtype=np.uint64), 3)
         key = (seed & 0xFFFFFFFF, ((seed >> 32) + int(k[i])) & 0xFFFFFFFF)
         out[i] = philox4x32(ctr, key, rounds)[0, int(j[i])]
     return out
@@ -299,7 +302,7 @@ def gswm_top_cell_words(seed: int, offset: int, latent_index: int, n_elems: int,
 
 def gswm_uniforms(seed: int, offset: int, latent_index: int, y: np.ndarray,
                   rounds: int = GSWM_PHILOX_ROUNDS) -> np.ndarray:
-    """float64 u in (0,1) for every element of one latent, given its bucket bits y ("gswm uniforms v3"):
+    """float64 u in (0,1) for every element of one latent, given its bucket bits y ("gswm uniforms v4"):
     v = (m + 1/2) 2^-23;  u = v where y == 1, u = 1 - v where y == 0 (both exact in float64).  An element in the
     outermost cell m = 2^23 - 1 is refined by 28 more bits: 1 - v = (m2 + 1/2) 2^-51, m2 = refinement word >> 4."""
     y = np.asarray(y).reshape(-1)

@@ -251,17 +251,17 @@ def test_gswm_uniform_source():
     assert chi2 < 340          # 255 dof: P(chi2 > 340) ~ 3e-4
     z = O.embed_gswm("lthero", KEY, NONCE, 0x5EED, 0, 0, 16384)
     assert O.bits_to_bytes(O.recover_message_bits(z, KEY, NONCE, 256))[:6] == b"lthero"
-    # uniforms v3: the outermost cell is subdivided (latent 74 of seed 0x5EED holds one such element, number 6852)
-    m = O.gswm_uniform_ints(0x5EED, 0, 74, 16384)
-    assert m[6852] == O.GSWM_TOP_CELL and (m == O.GSWM_TOP_CELL).sum() == 1
-    w = int(O.gswm_top_cell_words(0x5EED, 0, 74, 16384, [6852])[0])
+    # uniforms v3: the outermost cell is subdivided (latent 404 of seed 0x5EED holds one such element, number 503)
+    m = O.gswm_uniform_ints(0x5EED, 0, 404, 16384)
+    assert m[503] == O.GSWM_TOP_CELL and (m == O.GSWM_TOP_CELL).sum() == 1
+    w = int(O.gswm_top_cell_words(0x5EED, 0, 404, 16384, [503])[0])
     for ybit in (0, 1):
-        u = O.gswm_uniforms(0x5EED, 0, 74, np.full(16384, ybit))
+        u = O.gswm_uniforms(0x5EED, 0, 404, np.full(16384, ybit))
         tail = ((w >> 4) + 0.5) * 2.0 ** -51                      # 1 - v: exact in float64
-        assert u[6852] == (1.0 - tail if ybit else tail) and 0 < tail < 2.0 ** -23
+        assert u[503] == (1.0 - tail if ybit else tail) and 0 < tail < 2.0 ** -23
         zz = O.embed_from_uniform(np.full(16384, ybit), u)
-        assert 5.29 < abs(zz[6852]) <= 8.2096 and (zz[6852] > 0) == bool(ybit)
-        others = np.delete(np.arange(16384), 6852)
+        assert 5.29 < abs(zz[503]) <= 8.2096 and (zz[503] > 0) == bool(ybit)
+        others = np.delete(np.arange(16384), 503)
         v = (m[others] + 0.5) * 2.0 ** -23
         assert np.array_equal(u[others], v if ybit else 1 - v)
 
