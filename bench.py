@@ -376,7 +376,7 @@ def run_gpu_arm(args):
         B, first = hi - lo, lo
     else:                                              # weak scaling: every rank its own B latents
         B, first = args.batch, rank * args.batch
-    chunk = min(B, args.chunk_latents or max(1, (8 << 30) // (n * 4)))     # latents per launch (<= 8 GiB of fp32 per buffer)
+    chunk = min(B, args.chunk_latents or max(1, (1 << 30) // (n * 4)))     # latents per launch: 1 GiB of fp32 per buffer (8x the L2)
     pipeline = strong or chunk < B
     n_chunks = (B + chunk - 1) // chunk
     if args.per_latent_keys:
