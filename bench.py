@@ -68,8 +68,9 @@ def workload_name(args):
     keys = "per-latent key/nonce/message" if args.per_latent_keys else "shared default key/nonce, message 'lthero'"
     if getattr(args, "total_latents", None):
         which = "configs[4]" if args.per_latent_keys else "configs[3]"
-        return (f"BASELINE {which}: {args.total_latents} latents ({c}x{h}x{w}) in total, sharded over the GPUs, embed + extract "
-                f"round trip (per-sample noise, every message must decode exactly), {args.msg_bits}-bit message, {keys}")
+        return (f"BASELINE {which}: {args.total_latents} latents ({c}x{h}x{w}) in total, sharded over the GPUs: every GPU embeds its shard "
+                f"(per-sample noise) and extracts its shard of noisy latents (sigma={SIGMA}; every message must decode exactly), "
+                f"{args.msg_bits}-bit message, {keys}")
     return (f"BASELINE configs[1]+[2]: embed {args.batch} latents ({c}x{h}x{w}, per-sample noise) + extract {args.batch} "
             f"noisy latents (sigma={SIGMA}), {args.msg_bits}-bit message, {keys}")
 
@@ -376,8 +377,11 @@ def run_gpu_arm(args):
         B, first = hi - lo, lo
     else:                                              # weak scaling: every rank its own B latents
         B, first = args.batch, rank * args.batch
-    chunk = min(B, args.chunk_latents or max(1, (1 << 30) // (n * 4)))     # latents per launch: 1 GiB of fp32 per buffer (8x the L2)
-    pipeline = strong or chunk < B
+    # Both sides of a step stay RESIDENT when they fit (2 x B x n x 4 bytes <= 150 GB of the 180 GB): one launch per kernel, the
+    # two co-scheduled, exactly like the default workload.  A shard that does not fit is processed as a round trip in chunks.
+    fits = 2 * B * n * 4 <= 150e9 and not args.chunk_latents
+    chunk = B if fits else min(B, args.chunk_latents or max(1, (1 << 30) // (n * 4)))   # latents per launch
+    pipeline = chunk < B
     n_chunks = (B + chunk - 1) // chunk
     if args.per_latent_keys:
         rs = np.random.RandomState(2025)               # keys / nonces / messages from RandomState(2025).bytes
@@ -418,7 +422,11 @@ def run_gpu_arm(args):
         # BASELINE configs[1]+[2]: the extract side reads its own resident batch of noisy latents (sigma = 0.325)
         gswm._lib.check(lib.gswm_embed(C.byref(jobs[0][0]), seed, 0, first, z.data_ptr(), sp), "gswm_embed")
         g = torch.Generator(dev).manual_seed(99 + rank)
-        z_noisy = z + SIGMA * torch.randn(z.shape, device=dev, generator=g)
+        z_noisy = z.clone()
+        flat = z_noisy.view(-1)
+        for o in range(0, flat.numel(), 1 << 28):                  # 1 GiB slices: no batch-sized temporaries (the batch may be 69 GB)
+            sl = flat[o:o + (1 << 28)]
+            sl.add_(torch.randn(sl.shape, device=dev, generator=g), alpha=SIGMA)
     else:
         z_noisy = None
 
@@ -462,6 +470,8 @@ def run_gpu_arm(args):
             launch_embed(0, z, sp)
             launch_extract(0, z_noisy, sp if serial else xp, fused=last and comm is not None)
             return
+        serial = True          # measured: the chunked round trip gains nothing from two streams (embed of chunk c + 1 is resident
+                               # before extract of chunk c becomes eligible; tools/benchq.py sweep, profiles/r02_roundtrip_schedules.txt)
         for c in range(n_chunks):
             b_ = c & 1
             if c >= 2 and not serial:
@@ -728,7 +738,7 @@ def run_gpu_arm(args):
                    "latents_per_launch": burst_latents, "launches_per_step_per_kernel": n_chunks,
                    "l2": "inputs larger than L2 (%d MB streamed per step vs 126 MB L2)" % (step_bytes // 1000000) if step_bytes > 2 * 126e6 else
                          "WARNING: working set fits L2", "timing": "CUDA events on the launch stream (the extract stream is forked after the start event and joined before the end event), max over ranks; per-kernel durations: best (ms) and median (ms_median) of 3 bursts of %d back-to-back launches, each burst between one event pair" % inst_steps,
-                   "schedule": ("chunked round trip: extract decodes the chunk embed just wrote (noise-free), two buffers, embed of chunk k+1 co-scheduled with extract of chunk k on two CUDA streams"
+                   "schedule": ("chunked round trip on one stream: extract decodes the chunk embed just wrote (noise-free)"
                                 if pipeline else
                                 "embed and extract of a step run on two CUDA streams and share the SMs (FMA-bound embed next to HBM-bound extract); roofline.step.serial_ms is the same step on one stream"),
                    "collective": collective,
