@@ -180,7 +180,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "10"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -234,10 +234,15 @@ class ClockSampler:
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         inside = [r for r in rows if window and window[0] <= r[0] <= window[1]]
-        use = inside or rows
+        near = []
+        if window and not inside:                      # a window shorter than the sampling period: the two samples nearest to it
+            mid = window[0] + (window[1] - window[0]) / 2
+            near = sorted(rows, key=lambda r: abs((r[0] - mid).total_seconds()))[:2]
+        use = inside or near or rows
         return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)),
                 "reasons": sorted({nm for r in use for nm in r[4]}), "samples": len(use), "samples_total": len(rows),
-                "window": "timed region + per-kernel bursts" if inside else "whole run (no sample fell inside the timed window)",
+                "window": "timed region + per-kernel bursts" if inside else
+                          ("the two samples nearest to the timed region (it is shorter than the sampling period)" if near else "whole run"),
                 "power_w_max": max(r[3] for r in use)}
 
 
@@ -416,6 +421,7 @@ def run_gpu_arm(args):
     matched = torch.empty((chunk,), dtype=torch.int32, device=dev)
     counters = torch.zeros((NC,), dtype=torch.int64, device=dev)
     reduced = torch.zeros((NC,), dtype=torch.int64, device=dev)
+    rendezvous = torch.zeros((1,), dtype=torch.int64, device=dev)
     zbuf = [torch.empty((chunk, *shape), dtype=torch.float32, device=dev) for _ in range(2 if pipeline else 1)]
     z = zbuf[0]
     if not pipeline:
@@ -491,6 +497,10 @@ def run_gpu_arm(args):
         (north_star) -- is part of the timed region: fused into the last extract launch (gswm_comm), or one c10d all-reduce."""
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         joined = torch.cuda.Event()
+        if comm is not None and reduce:
+            # device-side rendezvous AHEAD of the start event: the host barrier releases the ranks tens of microseconds apart, and
+            # with a collective at the end of the region every rank would be charged the latest rank's late start
+            comm.allreduce_counters(rendezvous)
         t0.record(stream)
         xstream.wait_event(t0)
         for i in range(n_steps):

@@ -375,8 +375,8 @@ def test_webui_scripts_patch_and_restore_with_stub_webui(gswm, monkeypatch):
 
 
 def test_bench_clock_sampler_selects_samples_inside_the_timed_window():
-    """bench.py's nvidia-smi sampler: lines are parsed by timestamp, only those inside the timed window count (all of them
-    if none falls inside), throttle reasons are collected from the selected lines."""
+    """bench.py's nvidia-smi sampler: lines are parsed by timestamp, only those inside the timed window count (the two
+    nearest ones if none falls inside), throttle reasons are collected from the selected lines."""
     import datetime as dt
 
     sys.path.insert(0, ROOT)
@@ -403,8 +403,13 @@ def test_bench_clock_sampler_selects_samples_inside_the_timed_window():
     got = sampler_with(lines).stop((t(10), t(50)))
     assert got["samples"] == 2 and got["samples_total"] == 4 and got["sm_mhz"] == 1800.0 and got["sm_max_mhz"] == 1965.0
     assert got["reasons"] == ["sw_power_cap"] and got["power_w_max"] == 1001.0 and got["window"].startswith("timed region")
-    got = sampler_with(lines).stop((t(100), t(200)))                     # nothing inside: every sample is used, and says so
-    assert got["samples"] == 4 and got["window"].startswith("whole run") and got["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+    got = sampler_with(lines).stop((t(100), t(200)))                     # nothing inside: the two nearest samples, and says so
+    assert got["samples"] == 2 and got["window"].startswith("the two samples nearest") and got["sm_mhz"] == 1832.5
+    assert got["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+    got = sampler_with(lines).stop((t(21), t(23)))                       # a window between two samples: its neighbours
+    assert got["samples"] == 2 and got["sm_mhz"] == 1800.0 and got["reasons"] == ["sw_power_cap"]
+    got = sampler_with(lines).stop(None)                                 # no window at all: every sample
+    assert got["samples"] == 4 and got["window"] == "whole run"
     assert sampler_with(["garbage"]).stop(None)["reasons"] == ["no samples"]
     s = bench.ClockSampler(0)
     assert s.stop()["reasons"] == ["nvidia-smi unavailable"] and s.wait_ready(0.01) is False
