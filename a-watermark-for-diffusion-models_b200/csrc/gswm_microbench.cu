@@ -14,10 +14,14 @@
 
 namespace {
 
-constexpr int kIters = 2048;
+constexpr int kIters = 1024;
 constexpr int kMbThreads = 1024;
 
-#define CHAINS8(BODY) BODY(0) BODY(1) BODY(2) BODY(3) BODY(4) BODY(5) BODY(6) BODY(7)
+// 8 independent chains, 4 times over per loop iteration: 32 measured instructions (64 for the two-instruction mix) against
+// ~3 of loop overhead (the first version had 8 per iteration and read 0.70 warp-inst/clk for a one-cycle FFMA: 8 / 11)
+#define CHAINS8_ONCE(BODY) BODY(0) BODY(1) BODY(2) BODY(3) BODY(4) BODY(5) BODY(6) BODY(7)
+#define CHAINS8(BODY) CHAINS8_ONCE(BODY) CHAINS8_ONCE(BODY) CHAINS8_ONCE(BODY) CHAINS8_ONCE(BODY)
+constexpr int kRepeat = 4;
 
 template <int kind>
 __global__ void __launch_bounds__(kMbThreads) issue_rate_kernel(uint32_t* out, uint32_t seed, long long* cycles) {
@@ -38,7 +42,9 @@ __global__ void __launch_bounds__(kMbThreads) issue_rate_kernel(uint32_t* out, u
       CHAINS8(B)
 #undef B
     } else if (kind == GSWM_ISSUE_IMAD_WIDE) { // 32 x 32 -> 64 multiply (Philox)
-#define B(i) asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(w[i]) : "r"((uint32_t)w[i]));
+      // w = lo(w) * M + w: both halves of every product stay live and every multiply depends on the one before (a chain of plain mul.wide whose high
+      // halves are overwritten unread gets narrowed to 32-bit IMADs by ptxas and reads 1.5 cycles instead of 4)
+#define B(i) asm volatile("{.reg .b32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, 0xD2511F53, %0;}" : "+l"(w[i]));
       CHAINS8(B)
 #undef B
     } else if (kind == GSWM_ISSUE_LOP3) {      // three-input logic (Philox xor, bit assembly)
@@ -53,9 +59,29 @@ __global__ void __launch_bounds__(kMbThreads) issue_rate_kernel(uint32_t* out, u
 #define B(i) asm volatile("fma.rn.f32 %0, %0, 0f3F800347, 0f3A83126F;" : "+f"(f[i]));
       CHAINS8(B)
 #undef B
-    } else if (kind == GSWM_ISSUE_PHILOX_MIX) { // IMAD.WIDE + LOP3 alternating: the shape of a Philox round
-#define B(i) asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(w[i]) : "r"((uint32_t)w[i] ^ a[i])); \
-             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"((uint32_t)(w[i] >> 32)), "r"(seed));
+    } else if (kind == GSWM_ISSUE_PHILOX_MIX) { // IMAD.WIDE + one three-input LOP3 alternating, each feeding the other: the shape of a Philox round
+#define B(i) asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(w[i]) : "r"(a[i])); \
+             asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a[i]) : "r"((uint32_t)w[i]), "r"((uint32_t)(w[i] >> 32)), "r"(seed));
+      CHAINS8(B)
+#undef B
+    } else if (kind == GSWM_ISSUE_FFMA2_LOP3) {  // packed FMA next to independent logic: do the FMA and ALU pipes overlap?
+#define B(i) asm volatile("{.reg .b64 t,u,v; mov.b64 t,{%0,%1}; mov.b64 u,{%2,%2}; mov.b64 v,{%3,%3}; fma.rn.f32x2 t,t,u,v; mov.b64 {%0,%1},t;}" : "+f"(f[i]), "+f"(g[i]) : "f"(c), "f"(c)); \
+             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+      CHAINS8(B)
+#undef B
+    } else if (kind == GSWM_ISSUE_FFMA_IMAD_WIDE) {  // scalar FMA next to an independent wide multiply: FMA-lite under the FMA-heavy pipe?
+#define B(i) asm volatile("fma.rn.f32 %0, %0, 0f3F800347, 0f3A83126F;" : "+f"(f[i])); \
+             asm volatile("{.reg .b32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, 0xD2511F53, %0;}" : "+l"(w[i]));
+      CHAINS8(B)
+#undef B
+    } else if (kind == GSWM_ISSUE_FFMA2_IMAD_WIDE) { // packed FMA next to an independent wide multiply
+#define B(i) asm volatile("{.reg .b64 t,u,v; mov.b64 t,{%0,%1}; mov.b64 u,{%2,%2}; mov.b64 v,{%3,%3}; fma.rn.f32x2 t,t,u,v; mov.b64 {%0,%1},t;}" : "+f"(f[i]), "+f"(g[i]) : "f"(c), "f"(c)); \
+             asm volatile("{.reg .b32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, 0xD2511F53, %0;}" : "+l"(w[i]));
+      CHAINS8(B)
+#undef B
+    } else if (kind == GSWM_ISSUE_LOP3_IMAD_WIDE) {  // independent logic next to an independent wide multiply
+#define B(i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(seed)); \
+             asm volatile("{.reg .b32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, 0xD2511F53, %0;}" : "+l"(w[i]));
       CHAINS8(B)
 #undef B
     }
@@ -84,7 +110,7 @@ int run_kind(int per_step, int sms, uint32_t* d_out, long long* d_cycles, double
   std::vector<long long> cyc(sms);
   if ((err = cudaMemcpy(cyc.data(), d_cycles, sizeof(long long) * sms, cudaMemcpyDeviceToHost)) != cudaSuccess) return (int)err;
   std::sort(cyc.begin(), cyc.end());
-  const double warp_instr_per_smsp = (double)kIters * 8 * per_step * (kMbThreads / 32 / 4);
+  const double warp_instr_per_smsp = (double)kIters * 8 * kRepeat * per_step * (kMbThreads / 32 / 4);
   *rate = warp_instr_per_smsp / (double)cyc[sms / 2];
   *ghz = (double)cyc[sms - 1] / ((double)ms * 1e6);
   gswm::count_launch(); gswm::count_launch();
@@ -111,6 +137,10 @@ extern "C" int gswm_debug_issue_rate(int32_t kind, double* warp_inst_per_clk_per
     case GSWM_ISSUE_MUFU: rc = run_kind<GSWM_ISSUE_MUFU>(1, sms, d_out, d_cycles, warp_inst_per_clk_per_smsp, sm_ghz); break;
     case GSWM_ISSUE_FFMA_IMM: rc = run_kind<GSWM_ISSUE_FFMA_IMM>(1, sms, d_out, d_cycles, warp_inst_per_clk_per_smsp, sm_ghz); break;
     case GSWM_ISSUE_PHILOX_MIX: rc = run_kind<GSWM_ISSUE_PHILOX_MIX>(2, sms, d_out, d_cycles, warp_inst_per_clk_per_smsp, sm_ghz); break;
+    case GSWM_ISSUE_FFMA2_LOP3: rc = run_kind<GSWM_ISSUE_FFMA2_LOP3>(2, sms, d_out, d_cycles, warp_inst_per_clk_per_smsp, sm_ghz); break;
+    case GSWM_ISSUE_FFMA_IMAD_WIDE: rc = run_kind<GSWM_ISSUE_FFMA_IMAD_WIDE>(2, sms, d_out, d_cycles, warp_inst_per_clk_per_smsp, sm_ghz); break;
+    case GSWM_ISSUE_FFMA2_IMAD_WIDE: rc = run_kind<GSWM_ISSUE_FFMA2_IMAD_WIDE>(2, sms, d_out, d_cycles, warp_inst_per_clk_per_smsp, sm_ghz); break;
+    case GSWM_ISSUE_LOP3_IMAD_WIDE: rc = run_kind<GSWM_ISSUE_LOP3_IMAD_WIDE>(2, sms, d_out, d_cycles, warp_inst_per_clk_per_smsp, sm_ghz); break;
     default: rc = GSWM_E_RANGE;
   }
   cudaFree(d_out);

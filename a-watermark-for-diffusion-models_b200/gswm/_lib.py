@@ -24,7 +24,8 @@ CTR_MATCHED_BITS, CTR_TOTAL_BITS, CTR_EXACT_MSGS, CTR_TOTAL_MSGS, CTR_NAN_LATENT
 FLAG_NAN, FLAG_RANGE = 1, 2
 JOB_PER_LATENT, JOB_KEYS_IN_FLIGHT = 1, 2
 E_COMM = -6
-ISSUE_KINDS = {"FFMA2": 0, "IMAD.WIDE": 1, "LOP3": 2, "MUFU.LG2": 3, "FFMA(imm)": 4, "IMAD.WIDE+LOP3": 5}
+ISSUE_KINDS = {"FFMA2": 0, "IMAD.WIDE": 1, "LOP3": 2, "MUFU.LG2": 3, "FFMA(imm)": 4, "IMAD.WIDE+LOP3": 5,
+               "FFMA2|LOP3": 6, "FFMA|IMAD.WIDE": 7, "FFMA2|IMAD.WIDE": 8, "LOP3|IMAD.WIDE": 9}
 COMM_HANDLE_BYTES, COMM_MAX_VALUES, COMM_MAX_RANKS = 64, 8, 32
 
 EXPORTS = [

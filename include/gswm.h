@@ -116,7 +116,7 @@ int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int6
  * gs_insert.gs_watermark_init_noise's arithmetic (gs_insert.py:23-66; nodes.py:76-123) for a batch:
  * tile message, XOR ChaCha20 keystream, one uniform per element, z = Phi^-1((u + y) / 2), fp32 store.
  *
- * Uniform source ("gswm uniforms v3", csrc/gswm_math.cuh; restated in oracle/gs_oracle.py:gswm_uniforms): every
+ * Uniform source ("gswm uniforms v4", csrc/gswm_math.cuh; restated in oracle/gs_oracle.py:gswm_uniforms): every
  * element gets a 23-bit integer m from Philox4x32-7 keyed by `seed`, with the counter built from the GLOBAL
  * latent index first_latent + b (so a batch sharded over ranks produces the same latents as one big batch),
  * the tile, the position and `offset` (< 2^62).  v = (m + 1/2) 2^-23; u = v for bucket bit 1, u = 1 - v for
@@ -124,7 +124,8 @@ int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int6
  * (probability 2^-23 per element) is subdivided by 28 more Philox bits, v = 1 - (m2 + 1/2) 2^-51, so |z| reaches
  * 8.2095 = norm.ppf(1 - 2^-53), the largest value the reference's 53-bit uniforms produce for bucket 1 -- the
  * 23-bit grid alone would stop at 5.42.
- * d_out: [n_latents][n_elems] fp32, 16-byte aligned.  first_latent >= 0.
+ * d_out: [n_latents][n_elems] fp32, 16-byte aligned.  first_latent >= 0 and
+ * (first_latent + n_latents) * ceil(n_elems / 16384) < 2^52 (the counter holds 54 bits of latent / tile / position).
  */
 int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent,
                float* d_out, void* stream);
@@ -278,7 +279,11 @@ enum {
   GSWM_ISSUE_LOP3 = 2,       /* three-input logic                        */
   GSWM_ISSUE_MUFU = 3,       /* MUFU.LG2                                 */
   GSWM_ISSUE_FFMA_IMM = 4,   /* scalar FMA, immediate operands: the one-instruction-per-clock issue peak */
-  GSWM_ISSUE_PHILOX_MIX = 5  /* IMAD.WIDE + LOP3 alternating             */
+  GSWM_ISSUE_PHILOX_MIX = 5, /* IMAD.WIDE + LOP3 feeding each other (a Philox round's shape) */
+  GSWM_ISSUE_FFMA2_LOP3 = 6,      /* independent pairs: do the pipes overlap? (2 instructions per step) */
+  GSWM_ISSUE_FFMA_IMAD_WIDE = 7,
+  GSWM_ISSUE_FFMA2_IMAD_WIDE = 8,
+  GSWM_ISSUE_LOP3_IMAD_WIDE = 9
 };
 int gswm_debug_issue_rate(int32_t kind, double* warp_inst_per_clk_per_smsp, double* sm_ghz);
 
