@@ -425,6 +425,7 @@ __device__ __forceinline__ double horner64(const double (&c)[N], double x) {
 }
 
 __device__ inline double norm_ppf_f64(double p) {
+  if (!(p >= 0.0 && p <= 1.0)) return CUDART_NAN;                   // outside [0, 1] (or NaN): scipy's ndtri returns nan
   // t = 2 min(p, 1-p) in (0,1]; both branches are exact in binary64 for p in [0,1]
   const bool upper = p > 0.5;
   const double t = upper ? 2.0 - 2.0 * p : 2.0 * p;

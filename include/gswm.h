@@ -133,8 +133,9 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
 /*
  * Embed with injected uniforms: d_u[n_latents][n_elems] float64 in [0,1) takes the place of
  * np.random.uniform(0,1) / RandomState(seed).uniform(0,1) (gs_insert.py:62; nodes.py:114-117) and
- * z = Phi^-1((u + y)/2) is evaluated in float64 (gs_insert.py:64).  u_per_latent == 0 reuses one
- * row of uniforms for every latent.  out_dtype: GSWM_F32 (what every caller casts to, README.md:112)
+ * z = Phi^-1((u + y)/2) is evaluated in float64 (gs_insert.py:64).  u is not range-checked: u = 0 with bucket bit 0 gives
+ * -inf and a u outside [0, 1] that pushes (u + y)/2 outside [0, 1] gives NaN, exactly as scipy's norm.ppf does.
+ * u_per_latent == 0 reuses one row of uniforms for every latent.  out_dtype: GSWM_F32 (what every caller casts to, README.md:112)
  * or GSWM_F64 (what gs_insert.py:75 returns).
  */
 int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_latent, void* d_out,

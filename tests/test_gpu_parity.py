@@ -110,6 +110,12 @@ def test_norm_ppf_f64(gswm, cuda_device):
     e = rel_err(got, ref)
     print("fp64 ppf max rel err:", e.max())
     assert e.max() <= 1e-9
+    # outside [0, 1] (an injected "uniform" that is none): nan, as scipy's norm.ppf answers -- not +-inf
+    bad = np.array([-1e-300, -0.25, 1.0000000000000002, 2.5, np.nan, -np.inf, np.inf])
+    d_b = torch.from_numpy(bad).to(cuda_device)
+    d_bo = torch.empty_like(d_b)
+    assert lib.gswm_debug_norm_ppf(d_b.data_ptr(), bad.size, d_bo.data_ptr(), None) == 0
+    assert np.isnan(d_bo.cpu().numpy()).all() and np.isnan(O.ndtri(bad)).all()
 
 
 # ------------------------------------------------------------------------------------ K2 embed
@@ -831,7 +837,40 @@ def test_large_latent_index_seed_offset_and_longest_message(gswm, cuda_device):
         gswm.extract_batch(torch.zeros((1, 4, 128, 128), device=cuda_device), gswm.KeyMaterial.make(KEY, NONCE, None, 16384))
 
 
-# ------------------------------------------------------------------------------------ uniforms v3, generator pins
+def test_counter_word3_changes_inside_a_launch(gswm, cuda_device):
+    """Uniforms v4: the Philox counter carries T = (latent * tiles + tile) * 4 + super-iteration split over two words,
+    (T & 0xFFFFFF) next to the lane index and T >> 24 next to the call index.  The lane-independent half of the rounds is
+    tabulated per CTA from the T >> 24 word, so a launch that straddles a multiple of 2^24 must switch table entries in the
+    middle of a CTA's latent loop -- shared key (persistent grid, table per interval) and per-latent keys (table per latent)."""
+    shape, n, L = (4, 64, 64), 16384, 256
+    cross = 1 << 22                                                      # tiles = 1: T = 4 * latent crosses 2^24 here
+    first, b = cross - 300, 600
+    km = gswm.KeyMaterial.make(KEY, NONCE, gswm.pad_message("lthero", 32), L)
+    z = gswm.embed_batch(b, shape, km, 0x5EED, 0, first, cuda_device)
+    pick = [0, 1, 298, 299, 300, 301, 302, 599] + np.random.RandomState(5).randint(0, b, size=8).tolist()
+    zh = z[pick].cpu().numpy().reshape(len(pick), n)
+    for j, i in enumerate(pick):
+        ref = O.embed_gswm("lthero", KEY, NONCE, 0x5EED, 0, first + i, n, L)
+        assert np.array_equal(zh[j] >= 0, ref >= 0) and rel_err(zh[j], ref).max() <= REL_TOL, i
+    # the same latents from launches that start elsewhere (other CTA / interval mapping): bit-identical
+    assert torch.equal(gswm.embed_batch(7, shape, km, 0x5EED, 0, cross - 3, cuda_device), z[297:304])
+    rs = np.random.RandomState(77)
+    kb, nb, mb = rs.bytes(32 * 6), rs.bytes(16 * 6), rs.bytes(32 * 6)
+    kmp = gswm.KeyMaterial.make(kb, nb, mb, L)
+    zp = gswm.embed_batch(6, shape, kmp, 9, 0, cross - 3, cuda_device).cpu().numpy().reshape(6, n)
+    for i in range(6):
+        ref = O.embed_gswm(mb[32 * i:32 * i + 32], kb[32 * i:32 * i + 32], nb[16 * i:16 * i + 16], 9, 0, cross - 3 + i, n, L)
+        assert np.array_equal(zp[i] >= 0, ref >= 0) and rel_err(zp[i], ref).max() <= REL_TOL, i
+    # the counter holds 54 bits of T: the last latent that fits, and one more (a range error, not a wrapped counter)
+    last = (1 << 52) - 1
+    zl = gswm.embed_batch(1, shape, km, 1, 0, last, cuda_device).cpu().numpy().reshape(n)
+    ref = O.embed_gswm("lthero", KEY, NONCE, 1, 0, last, n, L)
+    assert np.array_equal(zl >= 0, ref >= 0) and rel_err(zl, ref).max() <= REL_TOL
+    with pytest.raises(gswm.GswmError):
+        gswm.embed_batch(2, shape, km, 1, 0, last, cuda_device)
+
+
+# ------------------------------------------------------------------------------------ uniforms v3 / v4, generator pins
 def test_top_cell_refinement_matches_oracle(gswm, cuda_device):
     """Uniforms v3: an element whose 23-bit m falls in the outermost cell (probability 2^-23) is refined by 28 more Philox
     bits, so |z| can reach 8.21 like the reference's 53-bit uniforms.  Latents 404, 812, 1399 and 1458 of seed 0x5EED each
