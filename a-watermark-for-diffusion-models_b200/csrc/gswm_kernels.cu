@@ -1152,7 +1152,7 @@ int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t firs
   a.off_lo = (uint32_t)offset; a.off_hi = (uint32_t)(offset >> 32);
   {
     const unsigned __int128 last = ((unsigned __int128)first_latent + (unsigned __int128)job->n_latents) * a.tiles_per_latent * 4u;
-    if (last >> 54) return GSWM_E_RANGE;                              // the counter holds 54 bits of (latent, tile, super-iteration)
+    if (last > ((unsigned __int128)1 << 54)) return GSWM_E_RANGE;     // `last` is one past the largest T: the counter holds 54 bits of it
     const uint64_t pa = 0xD2511F53ull * a.off_lo, pb = 0xCD9E8D57ull * a.off_hi;
     a.pl.a_hi = (uint32_t)(pa >> 32); a.pl.b_lo = (uint32_t)pb;
     a.pl.x0 = (uint32_t)(pb >> 32) ^ a.seed_lo;                       // round keys 0: (seed_lo, seed_hi)

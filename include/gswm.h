@@ -125,7 +125,7 @@ int gswm_chacha20_keystream(const uint8_t* d_keys, const uint8_t* d_nonces, int6
  * 8.2095 = norm.ppf(1 - 2^-53), the largest value the reference's 53-bit uniforms produce for bucket 1 -- the
  * 23-bit grid alone would stop at 5.42.
  * d_out: [n_latents][n_elems] fp32, 16-byte aligned.  first_latent >= 0 and
- * (first_latent + n_latents) * ceil(n_elems / 16384) < 2^52 (the counter holds 54 bits of latent / tile / position).
+ * (first_latent + n_latents) * ceil(n_elems / 16384) <= 2^52 (the counter holds 54 bits of latent / tile / position).
  */
 int gswm_embed(const gswm_job* job, uint64_t seed, uint64_t offset, int64_t first_latent,
                float* d_out, void* stream);
