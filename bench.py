@@ -567,6 +567,14 @@ def run_gpu_arm(args):
     burst_latents = jobs[0][2]
     kernels_end = _dt.datetime.now()
 
+    # ---- issue-rate denominators, same run, same GPU (SURVEY 8(d)) ---------------------------------------------------------
+    issue = None
+    if rank == 0 and not args.no_issue_rates:
+        issue = {}
+        for name, kind in gswm._lib.ISSUE_KINDS.items():
+            r_, g_ = C.c_double(), C.c_double()
+            if lib.gswm_debug_issue_rate(kind, C.byref(r_), C.byref(g_)) == 0:
+                issue[name] = {"warp_inst_per_clk_per_smsp": round(r_.value, 4), "sm_ghz": round(g_.value, 3)}
     # ---- sustained leg: >= --sustain-seconds of back-to-back steps, whatever --steps was --------------------------------
     sustained = None
     if args.sustain_seconds > 0:
@@ -580,14 +588,6 @@ def run_gpu_arm(args):
         sus_ms = s0.elapsed_time(s1) / n_sus
         sustained = {"steps": n_sus, "ms_per_step": sus_ms, "window": (sus_begin, sus_end)}
 
-    # ---- issue-rate denominators, same run, same GPU (SURVEY 8(d)) ---------------------------------------------------------
-    issue = None
-    if rank == 0 and not args.no_issue_rates:
-        issue = {}
-        for name, kind in gswm._lib.ISSUE_KINDS.items():
-            r_, g_ = C.c_double(), C.c_double()
-            if lib.gswm_debug_issue_rate(kind, C.byref(r_), C.byref(g_)) == 0:
-                issue[name] = {"warp_inst_per_clk_per_smsp": round(r_.value, 4), "sm_ghz": round(g_.value, 3)}
     barrier()
     clocks = sampler.stop((load_begin, kernels_end)) if rank == 0 else None     # timed region + per-kernel bursts; the sustained leg has its own window
     if rank == 0 and sustained is not None:
@@ -703,12 +703,14 @@ def run_gpu_arm(args):
     issue_view = None
     if issue and ipe and "FFMA(imm)" in issue:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        ghz = issue["FFMA(imm)"]["sm_ghz"]
+        # clock: what nvidia-smi saw DURING the timed region + bursts (the kernel's own condition); the microbenchmarks run after
+        # the sustained leg, on a power-capped GPU, and their own clock would understate the peak the bursts ran against
+        ghz = (clocks["sm_mhz"] / 1e3) if clocks and clocks.get("sm_mhz") else issue["FFMA(imm)"]["sm_ghz"]
         peak_wi = issue["FFMA(imm)"]["warp_inst_per_clk_per_smsp"] * 4 * sms * ghz * 1e9      # warp instructions / s, whole GPU
         ach_wi = ipe * burst_latents * n / (embed_ms * 1e-3)
         issue_view = {"achieved": ach_wi, "peak": peak_wi, "unit": "warp-inst/s", "frac": ach_wi / peak_wi,
                       "inst_per_element": round(ipe, 3), "inst_source": ipe_src,
-                      "peak_source": "gswm_debug_issue_rate(FFMA imm) in this run: %.3f warp-inst/clk/SMSP x 4 x %d SMs x %.3f GHz"
+                      "peak_source": "gswm_debug_issue_rate(FFMA imm) in this run: %.3f warp-inst/clk/SMSP x 4 x %d SMs x %.3f GHz (SM clock under load, nvidia-smi)"
                                      % (issue["FFMA(imm)"]["warp_inst_per_clk_per_smsp"], sms, ghz)}
     hbm_frac = dom["GBps"] / peak
     bound = "hbm"
