@@ -13,6 +13,42 @@ sys.path.insert(0, os.path.join(ROOT, "a-watermark-for-diffusion-models_b200"))
 import gswm  # noqa: E402
 
 
+def _own_nccl_comm(rank, world, dev):
+    """An ncclComm_t created with ctypes (ncclGetUniqueId on rank 0, broadcast through torch.distributed, ncclCommInitRank):
+    what a C host that owns a communicator would hand to gswm_allreduce_counters.  None if libnccl cannot be loaded."""
+    import ctypes as C
+    import glob
+    import site
+
+    cands = []
+    for sp in site.getsitepackages() + [os.path.dirname(os.path.dirname(torch.__file__))]:
+        cands += glob.glob(os.path.join(sp, "nvidia", "nccl", "lib", "libnccl.so*"))
+    lib = None
+    for path in cands + ["libnccl.so.2", "libnccl.so"]:
+        try:
+            lib = C.CDLL(path)
+            break
+        except OSError:
+            continue
+    if lib is None:
+        return None
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_byte * 128)]
+
+    uid = UniqueId()
+    if rank == 0:
+        assert lib.ncclGetUniqueId(C.byref(uid)) == 0
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    C.memmove(C.byref(uid), bytes(t.cpu().tolist()), 128)
+    comm = C.c_void_p()
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    assert lib.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    lib.ncclCommDestroy.argtypes = [C.c_void_p]
+    return lib, comm
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -42,10 +78,23 @@ def main():
     for _ in range(5):
         res = gswm.extract_batch(zn, km, comm=comm)
         assert torch.equal(res.reduced, want), (rank, res.reduced.tolist(), want.tolist())
-    # 3. NCCL through the C ABI gives the same sum (torch's communicator is not reachable from Python: c10d here)
+    # 3. the NCCL form: c10d's all-reduce, and gswm_allreduce_counters on a communicator of our own (torch's ncclComm_t is
+    #    not reachable from Python, so one is created through ctypes on the libnccl torch itself has loaded)
     nc = gswm.extract_batch(zn, km).counters.clone()
     dist.all_reduce(nc)
     assert torch.equal(nc, want)
+    nccl = _own_nccl_comm(rank, world, dev)
+    if nccl is not None:
+        lib, comm_ptr = nccl
+        mine = gswm.extract_batch(zn, km).counters.clone()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = gswm._lib.lib().gswm_allreduce_counters(comm_ptr, mine.data_ptr(), mine.numel(), st)
+        torch.cuda.synchronize(dev)
+        assert rc == 0 and torch.equal(mine, want), (rank, rc, mine.tolist())
+        assert gswm._lib.lib().gswm_allreduce_counters(None, mine.data_ptr(), 6, st) == -1          # GSWM_E_NULL
+        lib.ncclCommDestroy(comm_ptr)
+    elif rank == 0:
+        print("MGPU note: libnccl not loadable through ctypes, gswm_allreduce_counters not exercised", flush=True)
     # 4. ranks arriving at very different times (rank 0 late): the exchange waits, nothing is lost
     if rank == 0:
         torch.cuda._sleep(int(2e8))

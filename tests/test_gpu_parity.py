@@ -6,6 +6,7 @@ bit counts BIT-EXACT; latents within 1e-6 relative of scipy's float64 norm.ppf.
 """
 import ctypes as C
 import hashlib
+import os
 import types
 
 import numpy as np
@@ -19,6 +20,7 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-6   # north_star: latents within 1e-6 relative of scipy's float64 norm.ppf
 KEY = bytes.fromhex(O.DEFAULT_KEY_HEX)
 NONCE = bytes.fromhex(O.DEFAULT_NONCE_HEX)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -549,6 +551,22 @@ def test_config5_per_latent_keys_1m(gswm, cuda_device):
                 ref = O.embed_gswm(m, k, no, 2025, 0, g, n, L)
                 assert rel_err(zs[j], ref).max() <= REL_TOL
     assert list(counters.cpu().numpy()) == [total * L, total * L, total, total, 0, 0]
+
+
+def test_c_host_round_trip(gswm, cuda_device, tmp_path):
+    """tests/c_abi/roundtrip.c: a C program on the CUDA runtime alone (no Python, no torch) embeds, decodes and scores a batch
+    through libgswm.so, device API and host-buffer pipe, and checks known answers of the default key."""
+    import subprocess
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = tmp_path / "roundtrip"
+    libdir = os.path.dirname(gswm._lib.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", f"-I{os.path.join(ROOT, 'include')}", f"-I{cuda}/include",
+                         os.path.join(ROOT, "tests", "c_abi", "roundtrip.c"), "-o", str(exe), f"-L{libdir}", "-lgswm",
+                         f"-L{cuda}/lib64", "-lcudart", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{cuda}/lib64"],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "roundtrip ok" in run.stdout, run.stdout + run.stderr
 
 
 # ------------------------------------------------------------------------------------ host-buffer pipe
