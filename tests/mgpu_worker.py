@@ -107,7 +107,7 @@ def main():
     comm.close()
     dist.destroy_process_group()
     if rank == 0:
-        print("MGPU OK", world, want.tolist(), flush=True)
+        print("MGPU OK", world, want.tolist(), "nccl_c_abi=%d" % int(nccl is not None), flush=True)
 
 
 if __name__ == "__main__":

@@ -32,6 +32,7 @@ def test_comm_between_processes(world):
            "--master-port", str(29611 + world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "MGPU OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "nccl_c_abi=1" in res.stdout, "gswm_allreduce_counters was not exercised (libnccl not loadable through ctypes)"
 
 
 def test_comm_local_two_devices(gswm):
