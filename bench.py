@@ -347,7 +347,6 @@ def run_gpu_arm(args):
     os.dup2(2, 1)
     import ctypes as C
     import datetime as _dt
-    import threading
 
     import torch
     import torch.distributed as dist
@@ -630,11 +629,13 @@ def run_gpu_arm(args):
     e2e_steps = max(1, args.e2e_steps)
     box = {}
 
+    from concurrent.futures import ThreadPoolExecutor
+    embed_side = ThreadPoolExecutor(max_workers=1)      # one long-lived host thread for the D2H direction (no thread start per step)
+
     def e2e_step():
-        t = threading.Thread(target=lambda: pipe_e.embed(h_out, kme, seed, 0, first))
-        t.start()
+        fut = embed_side.submit(pipe_e.embed, h_out, kme, seed, 0, first)
         box["x"] = pipe_x.extract(h_in, kme)
-        t.join()
+        fut.result()
         return box["x"]
 
     e2e_step()
@@ -678,6 +679,7 @@ def run_gpu_arm(args):
     key_bytes = kme.keys.nbytes + kme.nonces.nbytes + (kme.msgs.nbytes if kme.msgs is not None else 0)
     h2d = Be * n * 4 + key_bytes * 2                  # latents in + key material once per pipe call
     d2h = Be * n * 4 + Be * (L // 8) + Be * 4 + Be + 8 * NC
+    embed_side.shutdown()
     pipe_e.close()
     pipe_x.close()
     os.sched_setaffinity(0, affinity0)
