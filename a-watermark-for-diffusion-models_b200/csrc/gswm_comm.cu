@@ -161,8 +161,14 @@ int gswm_extract_allreduce(const gswm_job* job, const void* d_z, int32_t z_dtype
   // argument errors must not consume an epoch: every rank's epochs advance in lock step
   int rc = gswm::check_job(job, true);
   if (rc) return rc;
-  if (job->n_latents == 0) return GSWM_E_SHAPE;
   CommDev d;
+  if (job->n_latents == 0) {
+    // a rank whose shard is empty still takes part in the collective (the others wait for it): no extraction, the
+    // accumulated counters go through the stand-alone exchange
+    GSWM_CUDA(cudaMemcpyAsync(d_reduced, d_counters, sizeof(int64_t) * GSWM_N_COUNTERS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if ((rc = device_view(c, &d))) return rc;
+    return gswm::comm_allreduce_launch(d, d_reduced, GSWM_N_COUNTERS, stream);
+  }
   if ((rc = device_view(c, &d))) return rc;
   rc = gswm::extract_impl(job, d_z, z_dtype, d_msg_out, d_counts, d_matched, d_flags, d_counters, &d, d_reduced, stream);
   if (rc) --c->epoch;                                                  // nothing was launched

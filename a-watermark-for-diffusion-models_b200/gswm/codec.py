@@ -341,8 +341,8 @@ def extract_batch(z: torch.Tensor, km: KeyMaterial, want_counts: bool = False,
         if counters is None:
             counters = torch.zeros((_lib.N_COUNTERS,), dtype=torch.int64, device=dev)
         res = ExtractResult(msgs, cnt, matched, counters, flags, km.msg_bits)
-        if b == 0 and comm is None:              # an empty batch is valid and launches nothing
-            return res
+        if b == 0 and comm is None:              # an empty batch is valid and launches nothing (with a communicator the
+            return res                           # rank still joins the exchange: the peers wait for it)
         args = (C.byref(dj.job), z.data_ptr(), _DTYPE_CODE[z.dtype], msgs.data_ptr(),
                 cnt.data_ptr() if cnt is not None else None, matched.data_ptr() if matched is not None else None,
                 flags.data_ptr(), counters.data_ptr())

@@ -196,7 +196,8 @@ int gswm_extract(const gswm_job* job, const void* d_z, int32_t z_dtype, uint8_t*
  *
  * gswm_extract_allreduce is gswm_extract with that exchange FUSED into the kernel: the last CTA to retire
  * publishes the accumulated d_counters and writes the sum over ranks to d_reduced[GSWM_N_COUNTERS]; d_counters
- * itself keeps this rank's own totals.  gswm_comm_allreduce_counters is the stand-alone form (in place,
+ * itself keeps this rank's own totals (a rank with n_latents == 0 decodes nothing and still takes part in the exchange).
+ * gswm_comm_allreduce_counters is the stand-alone form (in place,
  * n <= GSWM_COMM_MAX_VALUES).  A peer that does not show up within ~10 s makes the kernel give up:
  * gswm_comm_status() then returns GSWM_E_COMM and the reduced values are unspecified.
  *

@@ -1178,6 +1178,16 @@ def test_comm_allreduce_two_ranks_on_one_device(gswm, cuda_device):
     want = (ctrs[0] + ctrs[1]).tolist()
     assert reds[0].tolist() == want and reds[1].tolist() == want
     assert lib.gswm_comm_status(hs[0]) == 0
+    # a rank with an empty shard decodes nothing and still takes part: its accumulated counters are summed with the peer's
+    empty = gswm._lib.Job(0, 16384, 256, 0, jobs[1].job.keys, jobs[1].job.nonces, jobs[1].job.msgs)
+    assert lib.gswm_extract_allreduce(C.byref(jobs[0].job), zs[0].data_ptr(), 0, outs[0].data_ptr(), None, None, None,
+                                      ctrs[0].data_ptr(), hs[0], reds[0].data_ptr(), streams[0].cuda_stream) == 0
+    assert lib.gswm_extract_allreduce(C.byref(empty), None, 0, outs[1].data_ptr(), None, None, None,
+                                      ctrs[1].data_ptr(), hs[1], reds[1].data_ptr(), streams[1].cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert ctrs[0].tolist()[:4] == [4 * 700 * 256, 4 * 700 * 256, 4 * 700, 4 * 700] and ctrs[1].tolist()[3] == 3 * 300
+    want = (ctrs[0] + ctrs[1]).tolist()
+    assert reds[0].tolist() == want and reds[1].tolist() == want
     # argument errors do not consume an epoch (the ranks would fall out of step)
     bad = gswm._lib.Job(1, 16384, 640, 0, 16, 16, None)
     assert lib.gswm_extract_allreduce(C.byref(bad), zs[0].data_ptr(), 0, outs[0].data_ptr(), None, None, None, ctrs[0].data_ptr(),
