@@ -100,6 +100,13 @@ def main():
         torch.cuda._sleep(int(2e8))
     res = gswm.extract_batch(zn, km, comm=comm)
     assert torch.equal(res.reduced, want)
+    # 5. fewer latents than ranks: the last rank's shard is empty, it decodes nothing and still joins the exchange
+    small = world - 1
+    lo2, hi2 = gswm.sharding.shard_range(small, rank, world)
+    z2 = gswm.embed_batch(hi2 - lo2, shape, km, 7, 0, lo2, dev)
+    r2 = gswm.extract_batch(z2, km, comm=comm)
+    assert r2.reduced.tolist() == [small * L, small * L, small, small, 0, 0], (rank, r2.reduced.tolist())
+    assert (hi2 - lo2 == 0) == (rank == world - 1)
     torch.cuda.synchronize()
     assert comm.status() == 0
     assert 0.85 < float(want[0]) / float(want[1]) < 0.95 and int(want[3]) == total
