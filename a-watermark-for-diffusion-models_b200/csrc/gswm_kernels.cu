@@ -401,7 +401,12 @@ embed_injected_kernel(const EmbedArgs a, const double* __restrict__ u, int u_per
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_ks);
   const double* up = u + (u_per_latent ? latent * a.n_elems : 0) + tile_base;
   OutT* op = out + latent * a.n_elems + tile_base;
-  for (uint32_t e = threadIdx.x; e < n_el; e += kThreads) {
+  // gridDim.z CTAs share a tile (each stages the tile's keystream itself: 2.4 us on one warp, in parallel): a single
+  // latent -- every call of the reference-named drop-ins -- is 16 CTAs instead of one doing 16 384 float64 quantiles
+  // (~45 us of a 128 us call, tools/dropin_breakdown.py)
+  const uint32_t per = (n_el + gridDim.z - 1) / gridDim.z;
+  const uint32_t lo = blockIdx.z * per, hi = lo + per < n_el ? lo + per : n_el;
+  for (uint32_t e = lo + threadIdx.x; e < hi; e += kThreads) {
     const double y = (double)((s_bytes[e >> 3] >> (7 - (e & 7))) & 1u);
     const double p = (up[e] + y) / 2.0;                              // gs_insert.py:64, same roundings
     op[e] = (OutT)norm_ppf_f64(p);
@@ -1180,7 +1185,11 @@ int gswm_embed_injected(const gswm_job* job, const double* d_u, int32_t u_per_la
   if (job->n_latents == 0) return GSWM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   EmbedArgs a = make_embed_args(job);
-  const dim3 grid((unsigned)job->n_latents, tiles_of(job->n_elems));
+  // small jobs: several CTAs per tile, so that one latent is not one CTA (see the kernel)
+  const int64_t ctas = job->n_latents * (int64_t)tiles_of(job->n_elems);
+  unsigned split = 1;
+  while (split < 16 && ctas * split * 2 <= 296) split *= 2;
+  const dim3 grid((unsigned)job->n_latents, tiles_of(job->n_elems), split);
   const int upl = u_per_latent ? 1 : 0;
   if (out_dtype == GSWM_F32) {
     if (per_latent_of(job)) embed_injected_kernel<true, float><<<grid, kThreads, 0, st>>>(a, d_u, upl, (float*)d_out);

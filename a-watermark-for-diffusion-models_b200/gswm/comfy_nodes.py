@@ -7,6 +7,7 @@ functions work (and are tested) outside ComfyUI.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import _embed_common as common
@@ -37,11 +38,12 @@ def gs_watermark_init_noise(key_hex, nonce_hex, device, message, use_seed, rando
     key, nonce = codec.resolve_key_nonce(key_hex, nonce_hex)                        # nodes.py:90-99
     shape = (4, height // 8, width // 8)
     if int(use_seed) == 1:                                                          # nodes.py:52-53,117: RandomState(randomSeed)
-        z = common.embed_seeded(randomSeed, shape, key, nonce, k, bits, torch.float32)
+        z = common.embed_seeded(randomSeed, shape, key, nonce, k, bits, torch.float32)[0].cpu()
     else:                                                                           # nodes.py:115: numpy's global generator
-        z = common.embed_injected(common.draw_uniforms(n, False, None), shape, key, nonce, k, bits, 1, torch.float32)
+        z = torch.from_numpy(common.embed_injected_host(common.draw_uniforms(n, False, None), shape, key, nonce, k, bits, 1,
+                                                        np.float32)[0])
     _log(key, nonce, k, randomSeed, height, width, message_length)
-    return z[0].cpu()
+    return z
 
 
 def gs_watermark_init_noise_batch(key_hex, nonce_hex, message, batch_size, width, height, message_length=-1,
@@ -60,12 +62,12 @@ def gs_watermark_init_noise_batch(key_hex, nonce_hex, message, batch_size, width
         key, nonce = codec.resolve_key_nonce(key_hex, nonce_hex)
         ks.append(k), keys.append(key), nonces.append(nonce)
     u = common.draw_uniforms(n, False, None, copies=batch_size).reshape(batch_size, n)
-    z = common.embed_injected(u, (4, height // 8, width // 8), b"".join(keys), b"".join(nonces), b"".join(ks), bits,
-                              batch_size, torch.float32)
+    z = common.embed_injected_host(u, (4, height // 8, width // 8), b"".join(keys), b"".join(nonces), b"".join(ks), bits,
+                                   batch_size, np.float32)
     for i in range(batch_size):
         r = i if rows > 1 else 0
         _log(keys[r], nonces[r], ks[r], randomSeed, height, width, message_length)
-    return z.cpu()
+    return torch.from_numpy(z)
 
 
 def common_ksampler(model, seed, steps, cfg, sampler_name, scheduler, positive, negative, latent, denoise=1.0,

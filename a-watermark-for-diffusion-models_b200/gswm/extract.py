@@ -43,9 +43,16 @@ def _decode(reversed_latents, args, batched: bool):
     if (z.shape[1] * z.element_size()) % 16:
         z = z.to(torch.float32)                     # odd-sized 16-bit rows: the kernel fetches rows in 16-byte pieces (exact upcast)
     km = codec.KeyMaterial.make(args.key, args.nonce, None, msg_bits)
-    dev = z.device if z.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    res = codec.extract_batch(z.to(dev), km)
-    return res, res.flags.cpu().numpy()
+    if z.is_cuda:
+        res = codec.extract_batch(z, km)
+        return res, res.flags.cpu().numpy()
+    # a host tensor (what extract.py:48,70 hands over): the host-buffer pipe -- one pinned staging copy in, the decoded bytes
+    # and flags written straight to host memory by the kernel, no torch tensor in between
+    from . import _embed_common as common
+    with common._pipes_lock:
+        msgs, _, _, counters, flags = common.host_pipe(z.shape[1]).extract(z, km)
+    res = codec.ExtractResult(torch.from_numpy(msgs), None, None, torch.from_numpy(counters), torch.from_numpy(flags), msg_bits)
+    return res, flags
 
 
 def recover_exactracted_message(reversed_latents, args) -> str:

@@ -14,6 +14,7 @@ from datetime import datetime
 import numpy as np
 import torch
 
+from . import _embed_common as common
 from . import codec
 
 
@@ -39,11 +40,9 @@ def gs_watermark_init_noise(opt, message=""):
     k = codec.pad_message(message, 32)                                   # gs_insert.py:9-20
     key, nonce = codec.resolve_key_nonce(opt.key_hex, opt.nonce_hex)     # gs_insert.py:27-42
     u = np.random.uniform(0, 1, size=4 * 64 * 64)                        # gs_insert.py:62, one per element
-    km = codec.KeyMaterial.make(key, nonce, k, 256)
-    dev = torch.device("cuda", torch.cuda.current_device())
-    z = codec.embed_batch_injected(torch.from_numpy(u).to(dev), (4, 64, 64), km, 1, torch.float64)
+    z = common.embed_injected_host(u, (4, 64, 64), key, nonce, k, 256, 1, np.float64)
     _append_info(key, nonce, k)
-    return z[0].cpu().numpy()
+    return z[0]
 
 
 def gs_watermark_init_noise_batch(opt, message="", n_samples=1, seed=None, device=None, first_latent=0,

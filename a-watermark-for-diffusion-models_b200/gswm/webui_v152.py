@@ -33,12 +33,12 @@ def init_gs_Z_s_T():
     k = codec.pad_message(global_message, 32, use_repeat=int(global_use_repeat) == 1)
     key, nonce = codec.resolve_key_nonce(global_key, global_nonce)
     if global_use_randomSeed != 0:                                  # v1.5.2:27,75: rng = RandomState(global_randomSeed)
-        z = common.embed_seeded(global_randomSeed, (4, 64, 64), key, nonce, k, 256, torch.float64)
+        z = common.embed_seeded(global_randomSeed, (4, 64, 64), key, nonce, k, 256, torch.float64)[0].cpu().numpy()
     else:                                                           # v1.5.2:73: numpy's global generator
-        z = common.embed_injected(common.draw_uniforms(4 * 64 * 64, False, None), (4, 64, 64), key, nonce, k, 256, 1,
-                                  torch.float64)
+        z = common.embed_injected_host(common.draw_uniforms(4 * 64 * 64, False, None), (4, 64, 64), key, nonce, k, 256, 1,
+                                       np.float64)[0]
     common.append_info([f"key: {key.hex()}", f"nonce: {nonce.hex()}", f"randomSeed: {global_randomSeed}", f"message: {k.hex()}"])
-    return z[0].cpu().numpy()
+    return z
 
 
 def _shared_device():

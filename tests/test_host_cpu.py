@@ -296,11 +296,11 @@ def test_comfy_unseeded_batch_host_logic_follows_the_reference(gswm, golden, mon
     spec.loader.exec_module(mg)
     seen = {}
 
-    def fake_embed(u, latent_shape, key, nonce, k, msg_bits, n_latents, out_dtype, device=None):
+    def fake_embed(u, latent_shape, key, nonce, k, msg_bits, n_latents, out_dtype=np.float64):
         seen.update(u=u, shape=latent_shape, key=key, nonce=nonce, k=k, bits=msg_bits, n=n_latents)
-        return torch.zeros((n_latents, *latent_shape), dtype=out_dtype)
+        return np.zeros((n_latents, *latent_shape), dtype=out_dtype)
 
-    monkeypatch.setattr(common, "embed_injected", fake_embed)
+    monkeypatch.setattr(common, "embed_injected_host", fake_embed)
     monkeypatch.chdir(tmp_path)
     g = golden["gslatent_unseeded_random"]
     monkeypatch.setattr(os, "urandom", mg._FakeUrandom())
