@@ -986,6 +986,13 @@ def test_embed_mt19937_is_the_seeded_reference(gswm, cuda_device, golden, golden
         u = torch.from_numpy(np.random.RandomState(c["seed"]).uniform(size=n)).to(cuda_device)
         zi = gswm.embed_batch_injected(u, shape, km, 1, torch.float32).cpu().numpy().reshape(-1)
         assert np.array_equal(z, zi), c["name"]                  # same uniforms, same arithmetic: bit-identical
+        # the Python wrapper takes the generator + injected route for small batches; the fused C entry point itself:
+        from gswm.codec import _DeviceJob
+        dj = _DeviceJob(km, 1, n, cuda_device)
+        zf = torch.empty((1, n), dtype=torch.float32, device=cuda_device)
+        assert gswm._lib.lib().gswm_embed_mt19937(C.byref(dj.job), None, c["seed"], zf.data_ptr(), 0,
+                                                 torch.cuda.current_stream(cuda_device).cuda_stream) == 0
+        assert np.array_equal(zf.cpu().numpy().reshape(-1), z), c["name"]
     # a batch with one seed per latent and per-latent keys, float64 out
     rs = np.random.RandomState(12)
     b, shape, n, L = 9, (4, 64, 64), 16384, 256
@@ -993,6 +1000,12 @@ def test_embed_mt19937_is_the_seeded_reference(gswm, cuda_device, golden, golden
     keys, nonces, msgs = rs.bytes(32 * b), rs.bytes(16 * b), rs.bytes(32 * b)
     km = gswm.KeyMaterial.make(keys, nonces, msgs, L)
     z = gswm.embed_batch_mt19937(seeds, b, shape, km, torch.float64, cuda_device).cpu().numpy().reshape(b, n)
+    dj = _DeviceJob(km, b, n, cuda_device)
+    d_seeds = torch.from_numpy(seeds.astype(np.uint32).view(np.int32)).to(cuda_device)
+    zf = torch.empty((b, n), dtype=torch.float64, device=cuda_device)
+    assert gswm._lib.lib().gswm_embed_mt19937(C.byref(dj.job), d_seeds.data_ptr(), 0, zf.data_ptr(), 3,
+                                             torch.cuda.current_stream(cuda_device).cuda_stream) == 0
+    assert np.array_equal(zf.cpu().numpy(), z)                     # fused kernel == generator + injected route
     for i in range(b):
         ref = O.embed(msgs[32 * i:32 * i + 32], keys[32 * i:32 * i + 32], nonces[16 * i:16 * i + 16],
                       np.random.RandomState(int(seeds[i])).uniform(size=n), L)
