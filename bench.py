@@ -719,14 +719,15 @@ def run_gpu_arm(args):
     issue_view = None
     if issue and ipe and "FFMA(imm)" in issue:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        # clock: what nvidia-smi saw DURING the timed region + bursts (the kernel's own condition); the microbenchmarks run after
-        # the sustained leg, on a power-capped GPU, and their own clock would understate the peak the bursts ran against
-        ghz = (clocks["sm_mhz"] / 1e3) if clocks and clocks.get("sm_mhz") else issue["FFMA(imm)"]["sm_ghz"]
+        # clock: the one the microbenchmark measured IN its kernel (clock64 ticks / elapsed time), right after the bursts.  nvidia-smi
+        # keeps reporting 1965 MHz while the SMs really run at 1.83 .. 1.92 GHz, and the embed kernel's time follows the real clock
+        # to the percent (tools/clock_vs_embed.py: time x clock = 101.8 k cycles per launch, profiles/r02_clock_vs_embed.json)
+        ghz = issue["FFMA(imm)"]["sm_ghz"]
         peak_wi = issue["FFMA(imm)"]["warp_inst_per_clk_per_smsp"] * 4 * sms * ghz * 1e9      # warp instructions / s, whole GPU
         ach_wi = ipe * burst_latents * n / (embed_ms * 1e-3)
         issue_view = {"achieved": ach_wi, "peak": peak_wi, "unit": "warp-inst/s", "frac": ach_wi / peak_wi,
                       "inst_per_element": round(ipe, 3), "inst_source": ipe_src,
-                      "peak_source": "gswm_debug_issue_rate(FFMA imm) in this run: %.3f warp-inst/clk/SMSP x 4 x %d SMs x %.3f GHz (SM clock under load, nvidia-smi)"
+                      "peak_source": "gswm_debug_issue_rate(FFMA imm) in this run: %.3f warp-inst/clk/SMSP x 4 x %d SMs x %.3f GHz (SM clock measured in the microbenchmark kernel)"
                                      % (issue["FFMA(imm)"]["warp_inst_per_clk_per_smsp"], sms, ghz)}
     hbm_frac = dom["GBps"] / peak
     bound = "hbm"
