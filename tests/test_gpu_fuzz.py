@@ -2,6 +2,8 @@
 8 pixels: ragged tiles, several tiles), message lengths, batch sizes, first-latent offsets, seeds, shared or per-latent keys,
 every input type of the extract kernel.  Embed: bucket membership exact, values within 1e-6 relative; extract: per-position
 counts, decoded bytes, matched bits and counters bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -27,7 +29,7 @@ def _rel(got, ref):
     return np.abs(got - ref) / np.abs(ref)
 
 
-@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=int(os.environ.get("GSWM_FUZZ_EXAMPLES", "30")), deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(h=st.integers(1, 24), w=st.integers(1, 24), lsel=st.integers(0, 10 ** 6), b=st.integers(1, 40),
        first=st.integers(0, 2 ** 40), seed=st.integers(0, 2 ** 64 - 1), offset=st.integers(0, 2 ** 62 - 1),
        per_latent=st.booleans(), dtype=st.sampled_from(["f32", "f16", "bf16", "f64"]), sigma=st.sampled_from([0.0, 0.5, 3.0]),
