@@ -110,7 +110,7 @@ __device__ __forceinline__ void build_sign_lut(float4* lut) {
 }
 
 #ifndef GSWM_TOPCELL
-#define GSWM_TOPCELL 1      // 1: the outermost grid cell is refined (uniforms v3); 0: diagnostic build without (the cell's midpoint)
+#define GSWM_TOPCELL 1      // 1: the outermost grid cell is refined (since uniforms v3); 0: diagnostic build without (the cell's midpoint)
 #endif
 struct TopCellShared {      // the CTA's log of outermost-cell elements (gswm_math.cuh: TopCellLog)
   uint2 list[kTopCellSlots];
@@ -175,7 +175,7 @@ __device__ __forceinline__ void embed_super_iteration(const EmbedArgs& a, const 
                                                                     __byte_perm(sign_pack, 0u, 0x4440u | k))
                                 : my_sign[2u * s_bytes[i >> 1]];
 #endif
-    // uniforms v3: an element in the outermost grid cell is logged here and refined in the kernel's epilogue
+    // an element in the outermost grid cell is logged here and refined in the kernel's epilogue
 #if GSWM_TOPCELL
     const TopCellLog top{&s_top->count, s_top->list, latent_rel, i};
 #else
@@ -363,7 +363,7 @@ embed_kernel(const EmbedArgs a) {
     }
   }
 #if GSWM_TOPCELL
-  // Epilogue (uniforms v3): refine the outermost-cell elements this CTA logged -- one in 8.4 M, so almost always none.
+  // Epilogue: refine the outermost-cell elements this CTA logged -- one in 8.4 M, so almost always none.
   __syncthreads();                                                    // all stores and log entries of the CTA are done and visible to it
   const uint32_t logged = s_top.count < kTopCellSlots ? s_top.count : kTopCellSlots;
   for (uint32_t e = threadIdx.x; e < logged; e += kThreads) {

@@ -159,7 +159,7 @@ __device__ __forceinline__ void philox4x32_v4_calls3(uint4 (&out)[3], uint32_t c
 }
 
 // ------------------------------------------------------------------------------------------------
-// The product's uniform source ("gswm uniforms v3", restated in oracle/gs_oracle.py:gswm_uniforms).
+// The product's uniform source ("gswm uniforms v4", restated in oracle/gs_oracle.py:gswm_uniforms).
 //
 // Every element gets a 23-bit integer m; its uniform is
 //       u = v        if the element's bucket bit y is 1,        v = (m + 1/2) 2^-23
@@ -181,6 +181,10 @@ __device__ __forceinline__ void philox4x32_v4_calls3(uint4 (&out)[3], uint32_t c
 // bit 1 -- where the plain 23-bit grid stops at 5.42 (tail mass 6e-8 cut off).  The hot loop does not know about it: the
 // rare tail block LOGS such an element in shared memory and the CTA refines its logged elements once, after its last
 // latent (TopCellLog below, embed_kernel's epilogue).
+//
+// v4: the counter layout -- lane index in word 1, T = (latent, tile, super-iteration) split over words 1 and 3, the offset in
+// words 0 and 2 (philox4x32_v4_calls3 above): same generator, same use of its output words, 26 instead of 35 wide multiplies
+// per 16 elements.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t r;
@@ -282,7 +286,7 @@ __device__ __forceinline__ void quantile_front1(uint32_t fa, float& v, float& x)
 #define GSWM_QUANTILE_MODE 0      // 0: both pairs packed (FFMA2); 1: pair 0 packed, pair 1 scalar; 2: all scalar
 #endif
 
-// The outermost grid cell, refined (uniforms v3).  w: 32 fresh Philox bits; m2 = w >> 4 (28 bits);
+// The outermost grid cell, refined (since uniforms v3).  w: 32 fresh Philox bits; m2 = w >> 4 (28 bits);
 // p = P(|Z| > z) / 2 = (m2 + 1/2) 2^-52;  |z| = -Phi^-1(p) = R(sqrt(52 - lg2(m2 + 1/2)) - S1), R of degree 5 fitted like the
 // others (tools/fit_halfnormal_quantile.py: 1.9e-7 relative in emulated fp32), |z| in [5.29, 8.21].  Reached about once
 // per 8 M elements, from inside the rare tail block: ~15 instructions plus one Philox call there, nothing anywhere else.
