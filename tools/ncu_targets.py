@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE kernel variant of libgswm a few times so that ncu can capture it (tools/ncu_all.sh drives this):
-    python tools/ncu_targets.py {embed_shared|embed_per_latent|embed_injected|extract_f32|extract_f16|extract_bf16|
+    python tools/ncu_targets.py {embed_shared|embed_per_latent|embed_injected|mt19937|extract_f32|extract_f16|extract_bf16|
                                  extract_per_latent|keystream} [n_latents]
 B = 4096 SD-2.1 latents (4x64x64, 256-bit message) unless given; inputs are embedded + perturbed latents (sigma 0.325)."""
 import os
@@ -39,6 +39,9 @@ def main():
         for _ in range(reps):
             res = gswm.extract_batch(z, km)
         assert res.bit_accuracy() == 1.0
+    elif which == "mt19937":
+        for _ in range(reps):
+            gswm.embed_batch_mt19937(list(range(1000, 1000 + B)), B, shape, shared, torch.float32, dev)
     elif which == "keystream":
         for _ in range(reps):
             gswm.chacha20_keystream(per.keys.tobytes(), per.nonces.tobytes(), 2048, dev)
